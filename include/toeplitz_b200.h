@@ -1,0 +1,155 @@
+/* libtoeplitz_b200.so -- C ABI of the B200-native ToeplitzMatrices.jl hot path.
+ *
+ * This is the drop-in boundary: the entry points a Julia package extension
+ * (ext/ToeplitzMatricesB200Ext.jl) binds with `ccall` to dispatch
+ * LinearAlgebra.mul!/factorize/ldiv!/... on device-resident vectors.  Each entry
+ * cites the reference method it replaces (paths relative to the reference repo,
+ * ToeplitzMatrices.jl v0.8.5).  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *  - every function returns an int status (TB200_OK == 0); tb200_last_error() gives
+ *    the thread-local message for the last non-zero status.
+ *  - pointers are DEVICE pointers unless the name ends in _host or the parameter is
+ *    documented as host.  Matrices are column-major with leading dimension ld* in
+ *    ELEMENTS of their own dtype.
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it except
+ *    where stated (tb200_cgs/tb200_cg read convergence scalars back every iteration).
+ *  - dtype: element type of a vector/matrix, TB200_F32/F64/C32/C64.  The working
+ *    precision of a handle is that of its matrix (S = promote_type(float(T),
+ *    ComplexF32), src/linearalgebra.jl:125): vectors passed to a handle must have the
+ *    same precision (real or complex); the host layer casts mixed inputs.
+ *  - a handle owns its spectrum, twiddle tables and one workspace: use a handle from
+ *    one stream at a time (the reference's factorization has the same restriction
+ *    through its shared `tmp`, src/ToeplitzMatrices.jl:97-101).
+ *  - there is NO CPU fallback: unsupported inputs return TB200_UNSUPPORTED.
+ */
+#ifndef TOEPLITZ_B200_H
+#define TOEPLITZ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum tb200_status {
+    TB200_OK = 0,
+    TB200_DIM_MISMATCH = 1,   /* -> Julia DimensionMismatch */
+    TB200_BAD_ARG = 2,        /* -> ArgumentError */
+    TB200_UNSUPPORTED = 3,    /* -> ErrorException */
+    TB200_CUDA_ERR = 4,
+    TB200_OOM = 5
+};
+
+enum tb200_dtype { TB200_F32 = 0, TB200_F64 = 1, TB200_C32 = 2, TB200_C64 = 3 };
+
+enum tb200_kind {
+    TB200_TOEPLITZ = 0,   /* Toeplitz(vc, vr)              src/toeplitz.jl:7-18        */
+    TB200_SYMMETRIC = 1,  /* SymmetricToeplitz(v)          src/special.jl:44-76        */
+    TB200_CIRCULANT = 2,  /* Circulant(v)                  src/special.jl:44-76        */
+    TB200_LOWER = 3,      /* LowerTriangularToeplitz(v)                                */
+    TB200_UPPER = 4,      /* UpperTriangularToeplitz(v)                                */
+    TB200_HANKEL = 5      /* Hankel(v, (m,n))              src/hankel.jl:2-12          */
+};
+
+enum tb200_specop { TB200_OP_INV = 0, TB200_OP_PINV = 1, TB200_OP_SQRT = 2, TB200_OP_CONJ = 3, TB200_OP_COPY = 4 };
+
+typedef struct tb200_fact* tb200_handle_t;
+
+const char* tb200_version(void);
+const char* tb200_last_error(void);
+
+/* ---- factorize ------------------------------------------------------------------
+ * Replaces factorize(::Toeplitz) src/linearalgebra.jl:122-131, (::SymmetricToeplitz)
+ * :140-150, (::Circulant) :184-192, (::Lower/UpperTriangularToeplitz) :415-435, and for
+ * TB200_HANKEL the composition factorize(reverse(H, dims=2)) src/hankel.jl:112-121,133-137
+ * (the x-reversal is then applied inside tb200_mul).
+ * vc: first column (m entries); vr: first row (n entries, TOEPLITZ only, else NULL).
+ * SYMMETRIC/CIRCULANT/LOWER/UPPER: vc = v (n entries), m == n.  HANKEL: vc = v (m+n-1).
+ * The handle stores the spectrum of the zero-padded power-of-two circulant embedding
+ * (N' >= m+n-1); CIRCULANT keeps exact n-point semantics (n a power of two is the fast
+ * path; other n use a chirp-z (Bluestein) plan built on the same kernels).            */
+int tb200_factorize(int kind, int dtype, int64_t m, int64_t n, const void* vc, const void* vr,
+                    void* stream, tb200_handle_t* out);
+int tb200_factorize_host(int kind, int dtype, int64_t m, int64_t n, const void* vc_host,
+                         const void* vr_host, void* stream, tb200_handle_t* out);
+int tb200_destroy(tb200_handle_t h);
+/* size(F) src/special.jl:262-263; embedding length; dtype of the matrix */
+int tb200_info(tb200_handle_t h, int64_t* m, int64_t* n, int64_t* n_embed, int* dtype, int* kind);
+
+/* ---- mul! ------------------------------------------------------------------------
+ * y[:, j] = alpha * maybereal(A * x[:, j]) + beta * y[:, j],  j < ncols.
+ * Replaces mul!(y, ::ToeplitzFactorization, x, alpha, beta) src/linearalgebra.jl:42-80 and
+ * its matrix form :88-99 (the serial column loop becomes the batch axis), and the Hankel
+ * forms src/hankel.jl:133-137.  alpha/beta: (re, im) pairs, host.  beta == 0 means y is
+ * not read (:68-71).  A real ydtype requires a real matrix, real x and real alpha/beta
+ * (then the real part is taken, src/ToeplitzMatrices.jl:114-115).                      */
+int tb200_mul(tb200_handle_t h, void* y, int64_t ldy, int ydtype, const void* x, int64_t ldx, int xdtype,
+              int64_t ncols, const double alpha[2], const double beta[2], void* stream);
+/* same, HOST buffers: column chunks are staged host->device->host through pinned
+ * bounce buffers on internal streams, copies overlapped with compute.  Synchronous.  */
+int tb200_mul_host(tb200_handle_t h, void* y_host, int64_t ldy, int ydtype, const void* x_host, int64_t ldx,
+                   int xdtype, int64_t ncols, const double alpha[2], const double beta[2]);
+/* N = m+n-1 < 512 direct O(mn) product, no factorization: src/linearalgebra.jl:19-34   */
+int tb200_mul_direct(int kind, int dtype, int64_t m, int64_t n, const void* vc, const void* vr,
+                     void* y, int64_t ldy, int ydtype, const void* x, int64_t ldx, int xdtype,
+                     int64_t ncols, const double alpha[2], const double beta[2], void* stream);
+
+/* ---- Circulant spectral family ----------------------------------------------------
+ * ldiv!(C::CirculantFactorization, b) src/linearalgebra.jl:225-242 (+ matrix form :102-110,
+ * 3-arg ldiv!(x, F, b)): x = maybereal(ifft(fft(b) ./ spectrum)); x may alias b.         */
+int tb200_circ_ldiv(tb200_handle_t h, void* x, int64_t ldx, const void* b, int64_t ldb, int dtype,
+                    int64_t ncols, void* stream);
+/* eigvals(C) :286-287 -- natural-order spectrum, n complex values of the handle precision */
+int tb200_circ_spectrum(tb200_handle_t h, void* out, void* stream);
+/* inv(F) :250-253, adjoint(F) :214-215, and the spectral halves of pinv :276-284 /
+ * sqrt :311-315 -> a NEW handle (own storage; the reference shares tmp/dft).            */
+int tb200_circ_map(tb200_handle_t h, int op, double tol, void* stream, tb200_handle_t* out);
+/* A*B on factorizations :197-211 -> new handle holding specA .* specB                   */
+int tb200_circ_mul(tb200_handle_t a, tb200_handle_t b, void* stream, tb200_handle_t* out);
+/* vc = maybereal(ifft(spectrum)) -> first column of a Circulant (:208-210,247-248,282-283,313) */
+int tb200_circ_to_vc(tb200_handle_t h, void* vc_out, int out_dtype, void* stream);
+
+/* strang(A) :255-266 (which = 0) / chan(A) :267-274 (which = 1): v_out has n entries     */
+int tb200_precond_vector(int which, int kind, int dtype, int64_t n, const void* vc, const void* vr,
+                         void* v_out, void* stream);
+
+/* ---- batched Levinson / Durbin ------------------------------------------------------
+ * Column j of R/B/X/Y is one independent system (the batch axis is new).
+ * levinson!(x, r, b) src/directLinearSolvers.jl:100-121: T = SymToeplitz([1; r]),
+ * r has n-1 entries, b and x have n.  diag (nsys entries) or NULL: the normalising
+ * wrapper levinson(T::SymmetricToeplitz, b) :123-134 (r /= diag, x /= diag).
+ * durbin!(y, r) :15-28: r and y have n entries.  dtype TB200_F32 / TB200_F64.            */
+int tb200_levinson_batched(int dtype, int64_t n, int64_t nsys, const void* r, int64_t ldr,
+                           const void* b, int64_t ldb, void* x, int64_t ldx, const void* diag,
+                           void* stream);
+int tb200_durbin_batched(int dtype, int64_t n, int64_t nsys, const void* r, int64_t ldr,
+                         void* y, int64_t ldy, void* stream);
+
+/* ---- iterative solvers ---------------------------------------------------------------
+ * IterativeLinearSolvers.cgs src/iterativeLinearSolvers.jl:99-215 and cg :9-97 with A a
+ * factorized structured matrix and M a Circulant factorization (factorize(strang(A)) /
+ * factorize(chan(A)), src/linearalgebra.jl:133-136,152,399-402) or NULL (identity).
+ * x (in: start vector, out: solution) and b have n entries of `dtype`.  Outputs (host):
+ * err = final relative residual, iter, flag (0 converged, 1 max_it, -1 breakdown rho == 0).
+ * Synchronous on `stream`.                                                               */
+int tb200_cgs(tb200_handle_t A, tb200_handle_t M, void* x, const void* b, int dtype, int64_t n,
+              int max_it, double tol, double* err, int* iter, int* flag, void* stream);
+int tb200_cg(tb200_handle_t A, tb200_handle_t M, void* x, const void* b, int dtype, int64_t n,
+             int max_it, double tol, double* err, int* iter, int* flag, void* stream);
+
+/* ---- multi-GPU plumbing ----------------------------------------------------------------
+ * The only exchange on the path is the spectrum, once per factorization: rank 0
+ * factorizes, the other ranks create an empty handle of the same shape and the caller
+ * broadcasts `bytes` bytes at `ptr` (NCCL over NVLink).             */
+int tb200_factorize_empty(int kind, int dtype, int64_t m, int64_t n, void* stream, tb200_handle_t* out);
+int tb200_spectrum_buffer(tb200_handle_t h, void** ptr, int64_t* bytes);
+
+/* tuning / introspection: number of kernel launches issued by this library so far      */
+int64_t tb200_launch_count(void);
+int tb200_set_option(const char* name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOEPLITZ_B200_H */

@@ -1,0 +1,381 @@
+"""GPU parity tests: the CUDA path, called through the host mirror -> C ABI, against the
+CPU oracle on the same seeded inputs.  Tolerances are the north_star's: relative 2-norm
+error <= 1e-12 (Float64/ComplexF64) and <= 1e-5 (Float32/ComplexF32)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import toeplitz_oracle as O
+from oracle import build_oracle as OC
+
+pytestmark = pytest.mark.gpu
+
+TOL64, TOL32 = 1e-12, 1e-5
+
+
+@pytest.fixture(scope="module")
+def tb():
+    import toeplitz_b200 as tb
+    return tb
+
+
+def rel(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    den = np.linalg.norm(b.ravel())
+    return np.linalg.norm((a - b).ravel()) / (den if den > 0 else 1.0)
+
+
+def dev(a):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t
+
+
+def devmat(a):
+    """numpy (n, l) -> column-major CUDA tensor (n, l)."""
+    return torch.from_numpy(np.ascontiguousarray(a.T)).cuda().t()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def p(base, n, dtype=np.float64):
+    return (base ** np.arange(n)).astype(dtype)
+
+
+def tol_of(dtype):
+    return TOL32 if np.dtype(dtype) in (np.dtype(np.float32), np.dtype(np.complex64)) else TOL64
+
+
+def make_pair(tb, kind, n, dtype, m=None):
+    """(oracle matrix, device matrix) for the reference's coefficient recipes (test/runtests.jl:23-48)."""
+    m = n if m is None else m
+    if kind == "toeplitz":
+        vc, vr = p(0.9, m, dtype), p(0.4, n, dtype)
+        return O.Toeplitz(vc, vr), tb.Toeplitz(dev(vc), dev(vr))
+    v = p(0.9, n, dtype)
+    cls = {"symmetric": "SymmetricToeplitz", "circulant": "Circulant", "lower": "LowerTriangularToeplitz",
+           "upper": "UpperTriangularToeplitz"}[kind]
+    return getattr(O, cls)(v), getattr(tb, cls)(dev(v))
+
+
+KINDS = ["toeplitz", "symmetric", "circulant", "lower", "upper"]
+DTYPES = [np.float64, np.complex128, np.float32, np.complex64]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("dtype", DTYPES, ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("n", [101, 2000])
+def test_mul_matrix_and_adjoint(tb, kind, dtype, n):
+    """test/runtests.jl:50-55: A*X and A'*X, X an n x 5 matrix (FFT path even at n=101)."""
+    rng = np.random.default_rng(n)
+    Ao, Ad = make_pair(tb, kind, n, dtype)
+    rdt = np.zeros(1, dtype).real.dtype
+    X = rng.standard_normal((n, 5)).astype(rdt)
+    Y = host(tb.mul(Ad, devmat(X)))
+    assert rel(Y, O.matvec(Ao, X)) <= tol_of(dtype)
+    Ya = host(tb.mul(tb.adjoint(Ad), devmat(X)))
+    assert rel(Ya, O.matvec(Ao.adjoint(), X)) <= tol_of(dtype)
+    # complex right-hand sides, vector form (n=101 takes the direct N<512 path)
+    xc = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.result_type(dtype, np.complex64))
+    yc = host(tb.mul(Ad, dev(xc)))
+    assert rel(yc, O.matvec(Ao, xc)) <= tol_of(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=lambda d: np.dtype(d).name)
+def test_rectangular(tb, dtype):
+    """test/runtests.jl:83-95."""
+    rng = np.random.default_rng(1)
+    rdt = np.zeros(1, dtype).real.dtype
+    for m, n in ((2000, 101), (101, 2000)):
+        Ao, Ad = make_pair(tb, "toeplitz", n, dtype, m=m)
+        X = rng.standard_normal((n, 5)).astype(rdt)
+        assert rel(host(tb.mul(Ad, devmat(X))), O.matvec(Ao, X)) <= tol_of(dtype)
+        x = X[:, 0].copy()
+        assert rel(host(tb.mul(Ad, dev(x))), O.matvec(Ao, x)) <= tol_of(dtype)
+
+
+def test_mixed_types_exact(tb):
+    """test/runtests.jl:74-81 (exact small cases)."""
+    A = tb.Toeplitz(torch.tensor([1, 2]), torch.tensor([1, 2]))
+    assert A.dtype == torch.float64
+    y = tb.mul(A, torch.ones(2, dtype=torch.float64, device="cuda"))
+    assert np.array_equal(host(y), np.full(2, 3.0))
+    C = tb.Circulant(torch.arange(1, 4, dtype=torch.float32))
+    y = tb.mul(C, torch.ones(3, dtype=torch.float64, device="cuda"))
+    assert y.dtype == torch.float64 and np.array_equal(host(y), np.full(3, 6.0))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.complex64], ids=lambda d: np.dtype(d).name)
+def test_hankel(tb, dtype):
+    """test/runtests.jl:154-215."""
+    rng = np.random.default_rng(2)
+    H = tb.Hankel(torch.tensor([1.0, 2, 3, 4, 5]), vr=torch.tensor([5.0, 6, 7, 8, 9]))
+    x = torch.ones(5, dtype=torch.float64, device="cuda")
+    assert rel(host(tb.mul(H, x)), np.array([15.0, 20, 25, 30, 35])) <= 1e-14
+    rdt = np.zeros(1, dtype).real.dtype
+    for m, n in ((101, 101), (2000, 2000), (101, 2000), (2000, 101)):
+        vc = (0.9 ** np.arange(m - 1, -1, -1)).astype(dtype)
+        vr = (0.4 ** np.arange(n)).astype(dtype)
+        Ho = O.Hankel(vc, vr=vr)
+        Hd = tb.Hankel(dev(vc), vr=dev(vr))
+        X = rng.standard_normal((n, 5)).astype(rdt)
+        assert rel(host(tb.mul(Hd, devmat(X))), O.matvec(Ho, X)) <= tol_of(dtype)
+        assert rel(host(tb.mul(Hd, dev(X[:, 0].copy()))), O.matvec(Ho, X[:, 0].copy())) <= tol_of(dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128], ids=lambda d: np.dtype(d).name)
+def test_alpha_beta_and_nan_safety(tb, dtype):
+    """mul!(y, A, x, alpha, beta): beta == 0 must not read y (src/linearalgebra.jl:68-71)."""
+    rng = np.random.default_rng(3)
+    n = 700
+    Ao, Ad = make_pair(tb, "toeplitz", n, dtype)
+    X = rng.standard_normal((n, 3)).astype(dtype)
+    Y0 = rng.standard_normal((n, 3)).astype(dtype)
+    a, b = (1.5, -0.25) if np.dtype(dtype).kind == "f" else (1.5 - 0.5j, -0.25 + 2j)
+    Yd = devmat(Y0.copy())
+    tb.mul_(Yd, Ad, devmat(X), a, b)
+    Yo = np.asfortranarray(Y0.copy())
+    O.mul_mat(Yo, Ao, X, dtype(a) if np.dtype(dtype).kind == "f" else a, dtype(b) if np.dtype(dtype).kind == "f" else b)
+    assert rel(host(Yd), Yo) <= TOL64
+    Yn = devmat(np.full((n, 3), np.nan, dtype=dtype))
+    tb.mul_(Yn, Ad, devmat(X), a, False)
+    assert np.isfinite(host(Yn)).all()
+    assert rel(host(Yn), a * O.matvec(Ao, X)) <= TOL64
+    # a factorization can be reused (README.md:25-28)
+    F = tb.factorize(Ad)
+    assert rel(host(tb.mul(F, devmat(X))), O.matvec(Ao, X)) <= TOL64
+
+
+@pytest.mark.parametrize("n,cols,dtype", [(5000, 4, np.float64), (9000, 3, np.complex128), (40000, 5, np.float64),
+                                          (70000, 2, np.float32), (300000, 3, np.complex64)],
+                         ids=lambda v: str(v))
+def test_two_level_sizes(tb, n, cols, dtype):
+    """Embeddings too long for one shared-memory FFT take the three-kernel two-level path."""
+    rng = np.random.default_rng(n)
+    rdt = np.zeros(1, dtype).real.dtype
+    vc = rng.standard_normal(n).astype(dtype)
+    vr = rng.standard_normal(n).astype(dtype)
+    vr[0] = vc[0]
+    Ao, Ad = O.Toeplitz(vc, vr), tb.Toeplitz(dev(vc), dev(vr))
+    X = rng.standard_normal((n, cols)).astype(rdt if np.dtype(dtype).kind == "f" else dtype)
+    assert rel(host(tb.mul(Ad, devmat(X))), O.matvec(Ao, X)) <= tol_of(dtype)
+    Hv = rng.standard_normal(2 * n - 1).astype(dtype)
+    Ho, Hd = O.Hankel(Hv, (n, n)), tb.Hankel(dev(Hv), (n, n))
+    assert rel(host(tb.mul(Hd, dev(X[:, 0].copy()))), O.matvec(Ho, X[:, 0].copy())) <= tol_of(dtype)
+
+
+def test_c1_config_single_vector(tb):
+    """BASELINE config 1: Toeplitz{Float64} n = 2^16, one vector."""
+    n = 1 << 16
+    rng = np.random.default_rng(0)
+    for vc, vr in ((p(0.9, n), p(0.4, n)), (lambda a, b: (a, np.concatenate([a[:1], b[1:]])))(
+            np.random.default_rng(1).standard_normal(n), np.random.default_rng(2).standard_normal(n))):
+        x = rng.standard_normal(n)
+        y = host(tb.mul(tb.Toeplitz(dev(vc), dev(vr)), dev(x)))
+        assert rel(y, O.matvec(O.Toeplitz(vc, vr), x)) <= TOL64
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.complex64], ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("n", [64, 2048, 32768])
+def test_circulant_family(tb, dtype, n):
+    """src/linearalgebra.jl:183-315 on power-of-two sizes (incl. a two-level size)."""
+    rng = np.random.default_rng(n + 7)
+    tol = tol_of(dtype) * 10
+    v = p(0.9, n, dtype)
+    v2 = (rng.random(n) + 0.5).astype(dtype)
+    Co, Cd = O.Circulant(v), tb.Circulant(dev(v))
+    C2o, C2d = O.Circulant(v2), tb.Circulant(dev(v2))
+    Fo, Fd = O.factorize(Co), tb.factorize(Cd)
+    assert Fd.size() == (n, n) and Fd.size(1) == n
+    # eigvals: DFT order, fft(C.vc) == spectrum (test/runtests.jl:543)
+    assert rel(host(tb.eigvals(Cd)), np.fft.fft(v.astype(np.complex128))) <= tol
+    # ldiv! vector / matrix / 3-arg
+    B = (rng.standard_normal((n, 4)) + (1j * rng.standard_normal((n, 4)) if np.dtype(dtype).kind == "c" else 0)).astype(dtype)
+    Bo = np.asfortranarray(B.copy())
+    O.ldiv_mat(Co, Bo, O.circ_ldiv)
+    Bd = devmat(B.copy())
+    tb.ldiv_(Cd, Bd)
+    assert rel(host(Bd), Bo) <= tol
+    xo = torch.zeros(n, dtype=Bd.dtype, device="cuda")
+    tb.circ_ldiv_(Fd, dev(B[:, 0].copy()), out=xo)
+    assert rel(host(xo), Bo[:, 0]) <= tol
+    assert rel(host(tb.ldiv(Cd, dev(B[:, 1].copy()))), Bo[:, 1]) <= tol
+    # inv / pinv / sqrt / det / products
+    assert rel(host(tb.inv(Cd).vc), O.circ_inv(Co).vc) <= tol
+    assert rel(host(tb.pinv(Cd).vc), O.circ_pinv(Co).vc) <= tol
+    assert rel(host(tb.sqrt(C2d).vc), O.circ_sqrt(C2o).vc) <= tol
+    for ta in (False, True):
+        for tbb in (False, True):
+            Ao_ = Fo.adjoint() if ta else Fo
+            Bo_ = O.factorize(C2o).adjoint() if tbb else O.factorize(C2o)
+            Ad_ = tb.adjoint(Fd) if ta else Fd
+            Bd_ = tb.adjoint(tb.factorize(C2d)) if tbb else C2d
+            assert rel(host(tb.circ_mul(Ad_, Bd_).vc), O.circ_mul(Ao_, Bo_).vc) <= tol
+    # issue #47: inv(F) * C ~ I
+    e = rng.random(n).astype(np.zeros(1, dtype).real.dtype)
+    Iv = tb.circ_mul(tb.inv(Fd), Cd)
+    assert rel(host(tb.mul(Iv, dev(e))), e) <= tol
+    if n == 64:
+        assert rel(host(tb.det(C2d)).item(), O.circ_det(C2o)) <= (1e-3 if np.dtype(dtype) == np.complex64 else 1e-10)
+
+
+def test_circulant_identity_issue73(tb):
+    """test/runtests.jl:794-803 at the nearest supported size."""
+    n = 16
+    b = np.random.default_rng(6).random(n)
+    P = tb.Circulant(dev(np.eye(n)[0]))
+    F = tb.factorize(P)
+    x = torch.zeros(n, dtype=torch.float64, device="cuda")
+    tb.circ_ldiv_(F, dev(b), out=x)
+    assert rel(host(x), b) <= 1e-14
+
+
+def test_pinv_singular(tb):
+    """pinv of the all-ones circulant (test/runtests.jl:558-565)."""
+    n = 64
+    for dtype in (np.float64, np.complex128):
+        v = np.ones(n, dtype)
+        assert rel(host(tb.pinv(tb.Circulant(dev(v))).vc), O.circ_pinv(O.Circulant(v)).vc) <= 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 2, 8, 64, 129, 200, 384, 512, 700])
+def test_levinson_durbin_batched(tb, n):
+    """src/directLinearSolvers.jl:15-28,100-134 batched over columns, vs the C oracle."""
+    rng = np.random.default_rng(n)
+    nsys = 37
+    R = np.asfortranarray(rng.random((n, nsys)) / max(n, 2))          # diag-dominant recipe (test/runtests.jl:117)
+    Bm = np.asfortranarray(rng.standard_normal((n, nsys)))
+    if n >= 2:
+        Y = host(tb.durbin(devmat(R)))
+        assert rel(Y, OC.c_durbin_batched(R)) <= TOL64
+    Rl = np.asfortranarray(R[: n - 1, :]) if n > 1 else np.zeros((0, nsys), order="F")
+    X = tb.colmajor(n, nsys)
+    tb.levinson_(X, devmat(Rl) if n > 1 else tb.colmajor(0, nsys), devmat(Bm))
+    ref = OC.c_levinson_batched(Rl, Bm) if n > 1 else Bm.copy()
+    assert rel(host(X), ref) <= TOL64
+
+
+def test_levinson_reference_kernels(tb):
+    """The n = 8 kernels of test/runtests.jl:112-151, incl. the scaled-diagonal wrapper."""
+    n = 8
+    xg = np.linspace(-1, 1, n + 1)
+    g = np.random.default_rng(3)
+    for a in (g.random(n + 1) / n, np.exp(-np.abs(xg[0] - xg)), np.exp(-np.abs(xg[0] - xg) ** 2) / 2):
+        a = a.copy()
+        a[0] = 1
+        r = a[1:]
+        assert rel(host(tb.durbin(dev(r))), O.durbin(r)) <= 1e-10
+        b = g.standard_normal(n)
+        assert rel(host(tb.levinson(dev(r[:-1].copy()), dev(b))), O.levinson(r[:-1], b)) <= 1e-10
+        TS = 2.1 * np.concatenate([[1.0], r[:-1]])
+        xs = host(tb.levinson(tb.SymmetricToeplitz(dev(TS)), dev(b)))
+        assert rel(xs, np.linalg.solve(O.SymmetricToeplitz(TS).dense(), b)) <= 1e-9
+        Bm = g.standard_normal((n, 3))
+        Xs = host(tb.levinson(tb.SymmetricToeplitz(dev(TS)), devmat(Bm)))
+        assert rel(Xs, np.linalg.solve(O.SymmetricToeplitz(TS).dense(), Bm)) <= 1e-9
+
+
+def test_levinson_float32(tb):
+    rng = np.random.default_rng(11)
+    n, nsys = 256, 9
+    R = np.asfortranarray((rng.random((n - 1, nsys)) / n).astype(np.float32))
+    Bm = np.asfortranarray(rng.standard_normal((n, nsys)).astype(np.float32))
+    X = tb.colmajor(n, nsys, torch.float32)
+    tb.levinson_(X, devmat(R), devmat(Bm))
+    assert rel(host(X), OC.c_levinson_batched(R.astype(np.float64), Bm.astype(np.float64))) <= TOL32
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.complex64], ids=lambda d: np.dtype(d).name)
+def test_cgs_matches_oracle(tb, dtype):
+    """cgs + Strang on a KMS SymmetricToeplitz: same iterates (count, flag, residual) as the oracle."""
+    n = 4096
+    rng = np.random.default_rng(7)
+    v = p(0.5, n, dtype)
+    b = rng.standard_normal(n).astype(dtype)
+    Ao, Ad = O.SymmetricToeplitz(v), tb.SymmetricToeplitz(dev(v))
+    tol = 100 * np.finfo(np.float64).eps if np.dtype(dtype) != np.complex64 else 1e-5
+    xo, eo, ito, fo = O.cgs(Ao, np.zeros(n, dtype), b.copy(), O.factorize(O.strang(Ao)), 50, tol)
+    xd, ed, itd, fd = tb.cgs(Ad, torch.zeros(n, dtype=dev(b).dtype, device="cuda"), dev(b),
+                             tb.factorize(tb.strang(Ad)), 50, tol)
+    assert fd == fo and abs(itd - ito) <= 1
+    assert rel(host(xd), xo) <= (1e-10 if np.dtype(dtype) != np.complex64 else 1e-4)
+    assert ed <= max(10 * eo, tol)
+    # fixed iteration count (no convergence -> flag 1) keeps the iterates aligned
+    xo2, eo2, ito2, fo2 = O.cgs(Ao, np.zeros(n, dtype), b.copy(), O.factorize(O.strang(Ao)), 3, 0.0)
+    xd2, ed2, itd2, fd2 = tb.cgs(Ad, torch.zeros(n, dtype=dev(b).dtype, device="cuda"), dev(b),
+                                 tb.factorize(tb.strang(Ad)), 3, 0.0)
+    assert (itd2, fd2) == (ito2, fo2) == (3, 1)
+    assert rel(host(xd2), xo2) <= (1e-9 if np.dtype(dtype) != np.complex64 else 1e-3)
+
+
+def test_strang_chan(tb):
+    n = 1000
+    for kind in ("toeplitz", "symmetric", "lower", "upper"):
+        for dtype in (np.float64, np.complex128):
+            Ao, Ad = make_pair(tb, kind, n, dtype)
+            assert np.array_equal(host(tb.strang(Ad).vc), O.strang(Ao).vc)
+            assert rel(host(tb.chan(Ad).vc), O.chan(Ao).vc) <= 1e-15
+
+
+@pytest.mark.parametrize("kind", ["toeplitz", "symmetric", "lower", "upper", "circulant"])
+def test_ldiv_drivers(tb, kind):
+    """ldiv!(A, b): cgs+Strang / cg+Strang / cgs+Chan / spectral (test/runtests.jl:58-59,103-105)."""
+    n = 1024
+    rng = np.random.default_rng(9)
+    Ao, Ad = make_pair(tb, kind, n, np.float64)
+    B = rng.standard_normal((n, 2))
+    ref = np.linalg.solve(Ao.dense(), B)
+    Bd = devmat(B.copy())
+    tb.ldiv_(Ad, Bd)
+    assert rel(host(Bd), ref) <= np.sqrt(np.finfo(float).eps)
+    with pytest.raises(tb.ArgumentError):
+        tb.ldiv(Ad, dev(B[:, 0].astype(np.complex128)))
+
+
+def test_cg_early_return_quirk(tb):
+    """cg returns `nothing` when the start residual is already below tol (src/iterativeLinearSolvers.jl:57-59)."""
+    n = 1024
+    A = tb.SymmetricToeplitz(dev(p(0.5, n)))
+    b = torch.zeros(n, dtype=torch.float64, device="cuda")
+    assert tb.cg(A, torch.zeros_like(b), b, tb.strang(A), 10, 1e-10) is None
+    with pytest.raises(tb.ToeplitzB200Error):
+        tb.ldiv_(A, b)
+
+
+def test_errors(tb):
+    n = 600
+    A = tb.Toeplitz(dev(p(0.9, n)), dev(p(0.4, n)))
+    z = lambda k: torch.zeros(k, dtype=torch.float64, device="cuda")
+    with pytest.raises(tb.DimensionMismatch):
+        tb.mul_(z(n - 1), A, z(n))
+    with pytest.raises(tb.DimensionMismatch):
+        tb.mul_(z(n), A, z(n + 1))
+    with pytest.raises(tb.DimensionMismatch):
+        tb.mul_(tb.colmajor(n, 2), A, tb.colmajor(n, 3))
+    with pytest.raises(tb.DimensionMismatch):
+        tb.circ_ldiv_(tb.factorize(tb.Circulant(z(64) + 1)), z(65))
+    with pytest.raises(tb.ToeplitzB200Error):
+        tb.ldiv_(tb.Toeplitz(dev(p(0.9, 4)), dev(p(0.4, 3))), tb.colmajor(4, 1))
+    with pytest.raises(tb.ToeplitzB200Error):
+        tb.Toeplitz(dev(np.array([1.0, 2])), dev(np.array([2.0, 1])))
+    with pytest.raises(tb.DimensionMismatch):
+        tb.circ_mul(tb.Circulant(z(64) + 1), tb.Circulant(z(128) + 1))
+    with pytest.raises(tb.ArgumentError):
+        tb.mul_(z(n), A, z(n).to(torch.complex128))        # complex product into a real y
+
+
+def test_mul_host_pipeline(tb):
+    """tb200_mul_host: host buffers in, host buffers out, chunked + overlapped."""
+    n, l = 20000, 13
+    rng = np.random.default_rng(5)
+    vc, vr = p(0.9, n), p(0.4, n)
+    X = rng.standard_normal((n, l))
+    Xh = torch.from_numpy(np.ascontiguousarray(X.T)).pin_memory().t()
+    Yh = torch.empty((l, n), dtype=torch.float64).pin_memory().t()
+    F = tb.factorize_host(tb.Toeplitz, torch.from_numpy(vc), torch.from_numpy(vr))
+    tb.set_option("host_chunk_bytes", 1 << 20)        # force several chunks
+    tb.mul_host_(Yh, F, Xh)
+    tb.set_option("host_chunk_bytes", 256 << 20)
+    assert rel(Yh.numpy(), O.matvec(O.Toeplitz(vc, vr), X)) <= TOL64

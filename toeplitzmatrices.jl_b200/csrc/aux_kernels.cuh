@@ -1,0 +1,190 @@
+// O(n) helper kernels around the FFT passes: circulant-embedding builder (K4),
+// spectrum maps for the Circulant family, spectrum un-scramble (eigvals), Strang /
+// T. Chan circulant builders, the N < 512 direct product and the fused BLAS-1
+// kernels of the cgs / cg iterations (K6).
+#pragma once
+#include "fft_core.cuh"
+
+namespace tb {
+
+enum Kind : int { K_TOEPLITZ = 0, K_SYMMETRIC = 1, K_CIRCULANT = 2, K_LOWER = 3, K_UPPER = 4, K_HANKEL = 5 };
+enum SpecOp : int { OP_INV = 0, OP_PINV = 1, OP_SQRT = 2, OP_CONJ = 3, OP_COPY = 4 };
+
+template <typename R>
+__device__ __forceinline__ cx<R> load_a(const void* p, int is_cplx, long long i) {
+    if (is_cplx) return reinterpret_cast<const cx<R>*>(p)[i];
+    return mk<R>(reinterpret_cast<const R*>(p)[i], 0);
+}
+
+// Entry (i, j) of the structured matrix, 0-based (src/toeplitz.jl:47-55, src/hankel.jl:70-73).
+template <typename R>
+__device__ __forceinline__ cx<R> struct_entry(int kind, const void* vc, const void* vr, int a_cplx,
+                                              long long m, long long n, long long i, long long j) {
+    switch (kind) {
+    case K_HANKEL: return load_a<R>(vc, a_cplx, i + j);
+    case K_CIRCULANT: { long long d = i - j; if (d < 0) d += n; return load_a<R>(vc, a_cplx, d); }
+    case K_SYMMETRIC: { long long d = i - j; if (d < 0) d = -d; return load_a<R>(vc, a_cplx, d); }
+    case K_LOWER: { long long d = i - j; return d >= 0 ? load_a<R>(vc, a_cplx, d) : mk<R>(0, 0); }
+    case K_UPPER: { long long d = j - i; return d >= 0 ? load_a<R>(vc, a_cplx, d) : mk<R>(0, 0); }
+    default: { long long d = i - j; return d >= 0 ? load_a<R>(vc, a_cplx, d) : load_a<R>(vr, a_cplx, -d); }
+    }
+}
+
+// K4: c[idx], idx in [0, Np): first column of the circulant the matrix is embedded in.
+// Reference: factorize (src/linearalgebra.jl:126-128, 144-147, 188-189, 420-421, 430-432)
+// with zeros inserted between the column part and the reversed row part;
+// Hankel: the Toeplitz of reverse(H, dims=2) (src/hankel.jl:116-117) built directly from v.
+template <typename R>
+__global__ void k_embed(cx<R>* __restrict__ c, long long Np, int kind, const void* vc, const void* vr,
+                        int a_cplx, long long m, long long n) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < Np;
+         idx += (long long)gridDim.x * blockDim.x) {
+        cx<R> v = mk<R>(0, 0);
+        const long long d = Np - idx;   // row offset for the wrapped part
+        switch (kind) {
+        case K_TOEPLITZ:
+            if (idx < m) v = load_a<R>(vc, a_cplx, idx);
+            else if (d < n) v = load_a<R>(vr, a_cplx, d);
+            break;
+        case K_SYMMETRIC:
+            if (idx < m) v = load_a<R>(vc, a_cplx, idx);
+            else if (d < n) v = load_a<R>(vc, a_cplx, d);
+            break;
+        case K_CIRCULANT:
+            v = load_a<R>(vc, a_cplx, idx);
+            break;
+        case K_LOWER:
+            if (idx < n) v = load_a<R>(vc, a_cplx, idx);
+            break;
+        case K_UPPER:
+            if (idx == 0) v = load_a<R>(vc, a_cplx, 0);
+            else if (d < n) v = load_a<R>(vc, a_cplx, d);
+            break;
+        case K_HANKEL:                  // vc[i] = v[n-1+i], vr[d] = v[n-1-d]
+            if (idx < m) v = load_a<R>(vc, a_cplx, n - 1 + idx);
+            else if (d < n) v = load_a<R>(vc, a_cplx, n - 1 - d);
+            break;
+        }
+        c[idx] = v;
+    }
+}
+
+template <typename R>
+__device__ __forceinline__ cx<R> cinv(cx<R> z) {
+    // Smith's algorithm (what Julia's inv(::Complex) does, up to scaling details)
+    R a = z.x, b = z.y;
+    if (fabs(a) >= fabs(b)) {
+        R r = b / a, den = a + b * r;
+        return mk<R>((R)1 / den, -r / den);
+    }
+    R r = a / b, den = a * r + b;
+    return mk<R>(r / den, (R)-1 / den);
+}
+
+template <typename R>
+__device__ __forceinline__ cx<R> csqrt_(cx<R> z) {
+    // principal square root (Julia sqrt(::Complex) semantics: branch cut on the negative real axis)
+    R a = z.x, b = z.y;
+    if (a == 0 && b == 0) return mk<R>(0, b);
+    R r = hypot(a, b);
+    R t = sqrt((r + fabs(a)) / 2);
+    if (a >= 0) return mk<R>(t, b / (2 * t));
+    return mk<R>(fabs(b) / (2 * t), copysign(t, b));
+}
+
+// Elementwise map on a spectrum (layout-agnostic).  src/linearalgebra.jl:246,251,278-281,313,215.
+template <typename R>
+__global__ void k_spec_map(cx<R>* __restrict__ out, const cx<R>* __restrict__ in, long long N, int op, R tol) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N;
+         i += (long long)gridDim.x * blockDim.x) {
+        cx<R> z = in[i], o;
+        switch (op) {
+        case OP_INV: o = cinv<R>(z); break;
+        case OP_PINV: o = (hypot(z.x, z.y) < tol) ? mk<R>(0, 0) : cinv<R>(z); break;
+        case OP_SQRT: o = csqrt_<R>(z); break;
+        case OP_CONJ: o = mk<R>(z.x, -z.y); break;
+        default: o = z; break;
+        }
+        out[i] = o;
+    }
+}
+
+template <typename R>
+__global__ void k_spec_mul(cx<R>* __restrict__ out, const cx<R>* __restrict__ a, const cx<R>* __restrict__ b, long long N) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N;
+         i += (long long)gridDim.x * blockDim.x)
+        out[i] = cmul(a[i], b[i]);
+}
+
+// Natural-order spectrum out[k], k in [0, Np), from the private layout (eigvals,
+// src/linearalgebra.jl:286-287).  two_level: k = k1 + N1*k2, row p = pos1(k1).
+template <typename R>
+__global__ void k_unscramble(cx<R>* __restrict__ out, const cx<R>* __restrict__ spec, long long Np,
+                             int log2l1, int log2l2) {
+    PlanDims d2{log2l2};
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < Np;
+         k += (long long)gridDim.x * blockDim.x) {
+        long long off;
+        if (log2l1 == 0) {
+            off = d2.layout_of_pos(d2.pos_of_freq((int)k));
+        } else {
+            PlanDims d1{log2l1};
+            const int k1 = (int)(k & ((1LL << log2l1) - 1));
+            const int k2 = (int)(k >> log2l1);
+            const long long p = d1.pos_of_freq(k1);
+            off = (p << log2l2) + d2.layout_of_pos(d2.pos_of_freq(k2));
+        }
+        out[k] = spec[off];
+    }
+}
+
+// strang / chan (src/linearalgebra.jl:255-274), elementwise on device.
+template <typename R>
+__global__ void k_strang_chan(void* vout, int which, int kind, const void* vc, const void* vr, int a_cplx, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        cx<R> v;
+        if (which == 0) {      // strang: v[i] = A[i,1] for i <= n/2 (0-based), else A[1, n-i+1]
+            if (i <= n / 2) v = struct_entry<R>(kind, vc, vr, a_cplx, n, n, i, 0);
+            else v = struct_entry<R>(kind, vc, vr, a_cplx, n, n, 0, n - i);
+        } else {               // chan: ((n-i)*A[i,1] + i*A[1, min(n-i+1, n)]) / n   (0-based i)
+            cx<R> c0 = struct_entry<R>(kind, vc, vr, a_cplx, n, n, i, 0);
+            long long jj = n - i; if (jj > n - 1) jj = n - 1;      // 0-based column
+            cx<R> r0 = struct_entry<R>(kind, vc, vr, a_cplx, n, n, 0, jj);
+            const R w0 = (R)(n - i), w1 = (R)i, inv = (R)n;
+            v = mk<R>((w0 * c0.x + w1 * r0.x) / inv, (w0 * c0.y + w1 * r0.y) / inv);
+        }
+        if (a_cplx) reinterpret_cast<cx<R>*>(vout)[i] = v;
+        else reinterpret_cast<R*>(vout)[i] = v.x;
+    }
+}
+
+// Direct O(mn) product for N = m+n-1 < 512 (src/linearalgebra.jl:19-34): one thread per
+// output row, same accumulation order over j as the reference.  grid = (ceil(m/128), ncols).
+template <typename R>
+__global__ void k_direct_mul(void* y, long long ldy, int y_cplx, const void* x, long long ldx, int x_cplx,
+                             int kind, const void* vc, const void* vr, int a_cplx, long long m, long long n,
+                             cx<R> alpha, cx<R> beta, int has_beta) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long col = blockIdx.y;
+    if (i >= m) return;
+    cx<R> acc = mk<R>(0, 0);
+    if (has_beta) {
+        cx<R> y0 = y_cplx ? reinterpret_cast<cx<R>*>(y)[col * ldy + i]
+                          : mk<R>(reinterpret_cast<R*>(y)[col * ldy + i], 0);
+        acc = cmul(beta, y0);
+    }
+    for (long long j = 0; j < n; ++j) {
+        cx<R> xj = x_cplx ? reinterpret_cast<const cx<R>*>(x)[col * ldx + j]
+                          : mk<R>(reinterpret_cast<const R*>(x)[col * ldx + j], 0);
+        cx<R> tmp = cmul(alpha, xj);
+        cx<R> aij = (kind == K_HANKEL) ? struct_entry<R>(kind, vc, vr, a_cplx, m, n, i, j)
+                                       : struct_entry<R>(kind, vc, vr, a_cplx, m, n, i, j);
+        cx<R> pr = cmul(tmp, aij);
+        acc.x += pr.x; acc.y += pr.y;
+    }
+    if (y_cplx) reinterpret_cast<cx<R>*>(y)[col * ldy + i] = acc;
+    else reinterpret_cast<R*>(y)[col * ldy + i] = acc.x;
+}
+
+}  // namespace tb

@@ -1,0 +1,921 @@
+// libtoeplitz_b200.so: handles, plans and the extern "C" entry points of
+// include/toeplitz_b200.h.  Host-side orchestration only -- all arithmetic is in the
+// kernels of fft_kernels.cuh / aux_kernels.cuh / blas1.cuh / levinson.cu.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "capi_internal.h"
+#include "fft_launch.cuh"
+#include "aux_kernels.cuh"
+#include "blas1.cuh"
+
+namespace tb {
+
+// ---------------------------------------------------------------------------------------
+// errors, counters, options
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+static std::atomic<long long> g_group_bytes{48ll << 20};   // two-level scratch budget per group
+static std::atomic<long long> g_host_chunk_bytes{256ll << 20};
+
+int set_error(int status, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return status;
+}
+int cuda_status(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return TB200_OK;
+    if (e == cudaErrorMemoryAllocation) return set_error(TB200_OOM, "%s: %s", what, cudaGetErrorString(e));
+    return set_error(TB200_CUDA_ERR, "%s: %s", what, cudaGetErrorString(e));
+}
+void count_launch(int n) { g_launches += n; }
+
+#define TB_CUDA(call, what)                                   \
+    do {                                                      \
+        int st__ = cuda_status((call), what);                 \
+        if (st__ != TB200_OK) return st__;                    \
+    } while (0)
+#define TB_TRY(expr)                                          \
+    do {                                                      \
+        int st__ = (expr);                                    \
+        if (st__ != TB200_OK) return st__;                    \
+    } while (0)
+
+static inline bool dt_is_cplx(int dt) { return dt == TB200_C32 || dt == TB200_C64; }
+static inline int dt_prec(int dt) { return (dt == TB200_F64 || dt == TB200_C64) ? 1 : 0; }
+static inline size_t dt_size(int dt) { return (dt_prec(dt) ? 8 : 4) * (dt_is_cplx(dt) ? 2 : 1); }
+static inline bool dt_valid(int dt) { return dt >= 0 && dt <= 3; }
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+static int dev_alloc(std::shared_ptr<DevBuf>& out, size_t bytes, const char* what) {
+    auto b = std::make_shared<DevBuf>();
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&b->p, bytes);
+    if (e != cudaSuccess) { b->p = nullptr; return cuda_status(e, what); }
+    b->bytes = bytes;
+    out = b;
+    return TB200_OK;
+}
+
+static int num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+static inline unsigned ew_grid(long long n, int threads = 256) {
+    long long g = (n + threads - 1) / threads;
+    long long cap = (long long)num_sms() * 16;
+    return (unsigned)std::max(1ll, std::min(g, cap));
+}
+
+// ---------------------------------------------------------------------------------------
+// twiddle tables
+// ---------------------------------------------------------------------------------------
+template <typename R>
+static void fill_twiddles(std::vector<cx<R>>& v, long long count, long long stride, long long period) {
+    // v[k] = exp(-2 pi i (k*stride)/period), evaluated in long double on an exactly reduced argument
+    v.resize((size_t)count);
+    const long double twopi = 6.283185307179586476925286766559005768L;
+    for (long long k = 0; k < count; ++k) {
+        long long num = (k * stride) % period;
+        // reduce to the first octant for accuracy
+        long double frac = (long double)num / (long double)period;   // exact: period is a power of two
+        long double c = cosl(twopi * frac), s = sinl(twopi * frac);
+        // exact values on the axes / diagonals
+        if (num * 4 % period == 0) {
+            long long q = num * 4 / period;
+            c = (q == 0) ? 1 : (q == 2) ? -1 : 0;
+            s = (q == 1) ? 1 : (q == 3) ? -1 : 0;
+        }
+        v[(size_t)k] = mk<R>((R)c, (R)(-s));
+    }
+}
+
+struct TwTables {
+    std::shared_ptr<DevBuf> f32, f64;
+};
+static std::mutex g_tw_mutex;
+static TwTables g_tw[64];
+
+template <typename R>
+static int global_twiddles(const cx<R>** out) {
+    int dev = 0;
+    TB_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
+    std::lock_guard<std::mutex> lock(g_tw_mutex);
+    std::shared_ptr<DevBuf>& slot = (sizeof(R) == 8) ? g_tw[dev].f64 : g_tw[dev].f32;
+    if (!slot) {
+        std::vector<cx<R>> h;
+        fill_twiddles<R>(h, TWN, 1, TWN);
+        std::shared_ptr<DevBuf> b;
+        TB_TRY(dev_alloc(b, sizeof(cx<R>) * TWN, "twiddle table"));
+        TB_CUDA(cudaMemcpy(b->p, h.data(), sizeof(cx<R>) * TWN, cudaMemcpyHostToDevice), "twiddle upload");
+        slot = b;
+    }
+    *out = reinterpret_cast<const cx<R>*>(slot->p);
+    return TB200_OK;
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+// ---------------------------------------------------------------------------------------
+// the handle
+// ---------------------------------------------------------------------------------------
+struct tb200_fact {
+    int kind = 0, dtype = 0, prec = 0, a_real = 0, device = 0;
+    int64_t m = 0, n = 0, Np = 0;
+    int log2np = 0, two_level = 0, log2l1 = 0, log2l2 = 0, ta = 0;
+    int reverse_x = 0;
+    std::shared_ptr<DevBuf> spec, inv_spec, tw_lo, tw_hi, scratch;
+    int tw_hb = 0;
+    bool spec_valid = false;
+};
+
+namespace tb {
+
+static int next_log2(int64_t v) { int l = 0; while ((1ll << l) < v) ++l; return l; }
+
+static int make_plan(tb200_fact* h) {
+    const int l = h->log2np;
+    const int max_single = h->prec ? 12 : 13;
+    if (l < LOGE) return set_error(TB200_UNSUPPORTED, "embedding shorter than 16 is handled by tb200_mul_direct");
+    if (l <= max_single) {
+        h->two_level = 0; h->log2l1 = 0; h->log2l2 = l; h->ta = 0;
+        return TB200_OK;
+    }
+    const int l2max = h->prec ? 12 : 13;
+    int l1 = std::max(l - l2max, std::min(9, l / 2));
+    int l2 = l - l1;
+    const int l1max = h->prec ? 11 : 12;
+    if (l1 > l1max) { l1 = l1max; l2 = l - l1; }
+    if (l2 > (h->prec ? 13 : 14))
+        return set_error(TB200_UNSUPPORTED, "embedding length 2^%d exceeds the two-level plan (max 2^%d)", l,
+                         l1max + (h->prec ? 13 : 14));
+    if (l1 < 6) { l1 = 6; l2 = l - l1; }
+    const int full = 128 / (int)(h->prec ? 16 : 8);            // columns per 128-byte line
+    int ta = full;
+    const size_t esz = h->prec ? 16 : 8;
+    while (ta > 4 && ((size_t)1 << l1) * ta * esz > 128 * 1024) ta >>= 1;
+    h->two_level = 1; h->log2l1 = l1; h->log2l2 = l2; h->ta = ta;
+    // inter-level twiddles  w_Np^m = lo[m & mask] * hi[m >> hb]
+    h->tw_hb = (l + 1) / 2;
+    const long long nlo = 1ll << h->tw_hb, nhi = 1ll << (l - h->tw_hb);
+    if (h->prec) {
+        std::vector<cx<double>> lo, hi;
+        fill_twiddles<double>(lo, nlo, 1, 1ll << l);
+        fill_twiddles<double>(hi, nhi, nlo, 1ll << l);
+        TB_TRY(dev_alloc(h->tw_lo, lo.size() * 16, "level twiddles"));
+        TB_TRY(dev_alloc(h->tw_hi, hi.size() * 16, "level twiddles"));
+        TB_CUDA(cudaMemcpy(h->tw_lo->p, lo.data(), lo.size() * 16, cudaMemcpyHostToDevice), "level twiddle upload");
+        TB_CUDA(cudaMemcpy(h->tw_hi->p, hi.data(), hi.size() * 16, cudaMemcpyHostToDevice), "level twiddle upload");
+    } else {
+        std::vector<cx<float>> lo, hi;
+        fill_twiddles<float>(lo, nlo, 1, 1ll << l);
+        fill_twiddles<float>(hi, nhi, nlo, 1ll << l);
+        TB_TRY(dev_alloc(h->tw_lo, lo.size() * 8, "level twiddles"));
+        TB_TRY(dev_alloc(h->tw_hi, hi.size() * 8, "level twiddles"));
+        TB_CUDA(cudaMemcpy(h->tw_lo->p, lo.data(), lo.size() * 8, cudaMemcpyHostToDevice), "level twiddle upload");
+        TB_CUDA(cudaMemcpy(h->tw_hi->p, hi.data(), hi.size() * 8, cudaMemcpyHostToDevice), "level twiddle upload");
+    }
+    return TB200_OK;
+}
+
+static int ensure_scratch(tb200_fact* h, size_t bytes) {
+    if (h->scratch && h->scratch->bytes >= bytes) return TB200_OK;
+    h->scratch.reset();
+    return dev_alloc(h->scratch, bytes, "workspace");
+}
+
+// One description of "apply a spectrum to columns": covers mul!, ldiv!, factorize's FFT and to_vc.
+struct ConvCall {
+    const void* x = nullptr; long long ldx = 0; int x_mode = IO_CPLX; long long n_in = 0; int reverse_x = 0;
+    void* y = nullptr; long long ldy = 0; int y_mode = IO_CPLX; long long m_out = 0;
+    long long ncols = 0, nfft = 0;
+    const void* spec = nullptr;      // layout-order spectrum or null
+    int do_fwd = 1, do_inv = 1;
+    double scale = 1.0; double alpha[2] = {1, 0}, beta[2] = {0, 0}; int has_beta = 0;
+};
+
+template <typename R>
+static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
+    ConvArgs<R> a;
+    memset(&a, 0, sizeof(a));
+    const cx<R>* tw = nullptr;
+    TB_TRY(global_twiddles<R>(&tw));
+    a.tw = tw;
+    a.x = c.x; a.ldx = c.ldx; a.x_mode = c.x_mode; a.n_in = c.n_in; a.reverse_x = c.reverse_x;
+    a.y = c.y; a.ldy = c.ldy; a.y_mode = c.y_mode; a.m_out = c.m_out;
+    a.ncols = c.ncols; a.nfft = c.nfft;
+    a.spec = reinterpret_cast<const cx<R>*>(c.spec); a.spec_rows = 1;
+    a.do_fwd = c.do_fwd; a.do_inv = c.do_inv;
+    a.scale = (R)c.scale; a.alpha = mk<R>((R)c.alpha[0], (R)c.alpha[1]); a.beta = mk<R>((R)c.beta[0], (R)c.beta[1]);
+    a.has_beta = c.has_beta;
+    if (c.nfft <= 0) return TB200_OK;
+    if (!h->two_level) {
+        count_launch();
+        return cuda_status(launch_rows<R>(h->log2l2, a, num_sms(), s), "k_rows");
+    }
+    // ---- two-level: A (strided cols, fwd) -> B (rows: fwd * spec inv) -> C (strided cols, inv)
+    const long long Np = h->Np, N1 = 1ll << h->log2l1, N2 = 1ll << h->log2l2;
+    long long G = std::max(1ll, g_group_bytes.load() / (long long)(Np * sizeof(cx<R>)));
+    G = std::min(G, c.nfft);
+    TB_TRY(ensure_scratch(h, (size_t)G * Np * sizeof(cx<R>)));
+    cx<R>* scratch = reinterpret_cast<cx<R>*>(h->scratch->p);
+    a.scratch = scratch; a.log2n2 = h->log2l2;
+    a.tw_lo = reinterpret_cast<const cx<R>*>(h->tw_lo->p);
+    a.tw_hi = reinterpret_cast<const cx<R>*>(h->tw_hi->p);
+    a.tw_hb = h->tw_hb;
+    const size_t in_esz = (c.x_mode == IO_REAL || c.x_mode == IO_PAIR) ? sizeof(R) : sizeof(cx<R>);
+    const size_t out_esz = (c.y_mode == IO_REAL || c.y_mode == IO_PAIR) ? sizeof(R) : sizeof(cx<R>);
+    const long long cols_per_fft = (c.x_mode == IO_PAIR || c.y_mode == IO_PAIR) ? 2 : 1;
+    for (long long f0 = 0; f0 < c.nfft; f0 += G) {
+        const long long g = std::min(G, c.nfft - f0);
+        // pass A
+        if (c.do_fwd) {
+            ConvArgs<R> pa = a;
+            pa.nfft = g;
+            pa.ncols = c.ncols - f0 * cols_per_fft;
+            if (c.x_mode == IO_SPEC) return set_error(TB200_BAD_ARG, "internal: IO_SPEC input with forward transform");
+            pa.x = reinterpret_cast<const char*>(c.x) + (size_t)f0 * cols_per_fft * c.ldx * in_esz;
+            count_launch();
+            TB_CUDA(launch_colsA<R>(h->log2l1, h->ta, pa, s), "k_colsA");
+        }
+        // pass B: rows of the scratch, in place
+        {
+            ConvArgs<R> pb = a;
+            pb.nfft = g * N1; pb.ncols = g * N1;
+            pb.n_in = N2; pb.reverse_x = 0; pb.m_out = N2;
+            pb.ldx = N2; pb.ldy = N2;
+            pb.x = scratch; pb.x_mode = IO_CPLX; pb.y = scratch; pb.y_mode = IO_CPLX;
+            pb.spec_rows = (int)N1;
+            pb.scale = (R)1; pb.alpha = mk<R>(1, 0); pb.beta = mk<R>(0, 0); pb.has_beta = 0;
+            if (!c.do_fwd) {             // inverse only: rows come from a layout-order spectrum
+                pb.x = c.x; pb.x_mode = IO_SPEC; pb.spec = nullptr;
+                if (g != 1 || c.nfft != 1) return set_error(TB200_BAD_ARG, "internal: inverse-only runs one transform");
+            }
+            if (!c.do_inv) {             // forward only: rows go out in layout order
+                pb.y = c.y; pb.y_mode = IO_SPEC; pb.spec = nullptr;
+                if (g != 1 || c.nfft != 1) return set_error(TB200_BAD_ARG, "internal: forward-only runs one transform");
+            }
+            count_launch();
+            TB_CUDA(launch_rows<R>(h->log2l2, pb, num_sms(), s), "k_rows (pass B)");
+        }
+        // pass C
+        if (c.do_inv) {
+            ConvArgs<R> pc = a;
+            pc.nfft = g;
+            pc.ncols = c.ncols - f0 * cols_per_fft;
+            pc.y = reinterpret_cast<char*>(c.y) + (size_t)f0 * cols_per_fft * c.ldy * out_esz;
+            count_launch();
+            TB_CUDA(launch_colsC<R>(h->log2l1, h->ta, pc, s), "k_colsC");
+        }
+    }
+    return TB200_OK;
+}
+
+static int run_conv(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
+    return h->prec ? run_conv_t<double>(h, c, s) : run_conv_t<float>(h, c, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// factorize
+// ---------------------------------------------------------------------------------------
+static int check_factorize_args(int kind, int dtype, int64_t m, int64_t n, const void* vc, const void* vr, bool need_ptrs) {
+    if (kind < 0 || kind > 5) return set_error(TB200_BAD_ARG, "unknown matrix kind %d", kind);
+    if (!dt_valid(dtype)) return set_error(TB200_BAD_ARG, "unknown dtype %d", dtype);
+    if (m <= 0 || n <= 0) return set_error(TB200_BAD_ARG, "matrix size must be positive, got %lldx%lld", (long long)m, (long long)n);
+    if (kind != TB200_TOEPLITZ && kind != TB200_HANKEL && m != n)
+        return set_error(TB200_DIM_MISMATCH, "matrix kind %d must be square, got %lldx%lld", kind, (long long)m, (long long)n);
+    if (need_ptrs) {
+        if (!vc) return set_error(TB200_BAD_ARG, "vc is NULL");
+        if (kind == TB200_TOEPLITZ && !vr) return set_error(TB200_BAD_ARG, "vr is NULL for a general Toeplitz matrix");
+    }
+    return TB200_OK;
+}
+
+static int new_handle(int kind, int dtype, int64_t m, int64_t n, tb200_fact** out) {
+    std::unique_ptr<tb200_fact> h(new tb200_fact());
+    h->kind = kind; h->dtype = dtype; h->prec = dt_prec(dtype); h->a_real = !dt_is_cplx(dtype);
+    h->m = m; h->n = n;
+    TB_CUDA(cudaGetDevice(&h->device), "cudaGetDevice");
+    if (kind == TB200_CIRCULANT) {
+        if ((n & (n - 1)) != 0)
+            return set_error(TB200_UNSUPPORTED,
+                             "Circulant of size %lld: only power-of-two sizes are implemented (Bluestein is SURVEY 8f)", (long long)n);
+        h->Np = n;
+    } else {
+        h->Np = 1ll << next_log2(m + n - 1);
+    }
+    if (h->Np < E) h->Np = E;
+    if (kind == TB200_CIRCULANT && h->Np != n)
+        return set_error(TB200_UNSUPPORTED, "Circulant of size %lld < 16: use tb200_mul_direct / dense algebra", (long long)n);
+    h->log2np = next_log2(h->Np);
+    h->reverse_x = (kind == TB200_HANKEL);
+    TB_TRY(make_plan(h.get()));
+    TB_TRY(dev_alloc(h->spec, (size_t)h->Np * (h->prec ? 16 : 8), "spectrum"));
+    *out = h.release();
+    return TB200_OK;
+}
+
+template <typename R>
+static int factorize_t(tb200_fact* h, const void* vc, const void* vr, cudaStream_t s) {
+    // K4: embedding into the workspace, then forward FFT into the layout-order spectrum
+    TB_TRY(ensure_scratch(h, (size_t)h->Np * sizeof(cx<R>)));
+    cx<R>* c = reinterpret_cast<cx<R>*>(h->scratch->p);
+    k_embed<R><<<ew_grid(h->Np), 256, 0, s>>>(c, h->Np, h->kind, vc, vr, !h->a_real, h->m, h->n);
+    count_launch();
+    TB_CUDA(cudaGetLastError(), "k_embed");
+    ConvCall cc;
+    cc.x = c; cc.ldx = h->Np; cc.x_mode = IO_CPLX; cc.n_in = h->Np;
+    cc.y = h->spec->p; cc.ldy = h->Np; cc.y_mode = IO_SPEC; cc.m_out = h->Np;
+    cc.ncols = 1; cc.nfft = 1; cc.do_fwd = 1; cc.do_inv = 0;
+    TB_TRY(run_conv_t<R>(h, cc, s));
+    h->spec_valid = true;
+    return TB200_OK;
+}
+
+static int mode_for(bool cplx) { return cplx ? IO_CPLX : IO_REAL; }
+
+}  // namespace tb
+
+extern "C" {
+
+const char* tb200_version(void) { return "toeplitz_b200 0.1.0 (sm_100a)"; }
+const char* tb200_last_error(void) { return g_err; }
+int64_t tb200_launch_count(void) { return g_launches.load(); }
+
+int tb200_set_option(const char* name, int64_t value) {
+    if (!name) return set_error(TB200_BAD_ARG, "option name is NULL");
+    if (!strcmp(name, "group_bytes")) { g_group_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
+    if (!strcmp(name, "host_chunk_bytes")) { g_host_chunk_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
+    return set_error(TB200_BAD_ARG, "unknown option '%s'", name);
+}
+
+int tb200_factorize_empty(int kind, int dtype, int64_t m, int64_t n, void* stream, tb200_handle_t* out) {
+    (void)stream;
+    if (!out) return set_error(TB200_BAD_ARG, "out is NULL");
+    TB_TRY(check_factorize_args(kind, dtype, m, n, nullptr, nullptr, false));
+    tb200_fact* h = nullptr;
+    TB_TRY(new_handle(kind, dtype, m, n, &h));
+    h->spec_valid = true;          // the caller fills the spectrum buffer (broadcast)
+    *out = h;
+    return TB200_OK;
+}
+
+int tb200_factorize(int kind, int dtype, int64_t m, int64_t n, const void* vc, const void* vr, void* stream,
+                    tb200_handle_t* out) {
+    if (!out) return set_error(TB200_BAD_ARG, "out is NULL");
+    TB_TRY(check_factorize_args(kind, dtype, m, n, vc, vr, true));
+    tb200_fact* h = nullptr;
+    TB_TRY(new_handle(kind, dtype, m, n, &h));
+    int st = h->prec ? factorize_t<double>(h, vc, vr, (cudaStream_t)stream) : factorize_t<float>(h, vc, vr, (cudaStream_t)stream);
+    if (st != TB200_OK) { delete h; return st; }
+    *out = h;
+    return TB200_OK;
+}
+
+int tb200_factorize_host(int kind, int dtype, int64_t m, int64_t n, const void* vc_host, const void* vr_host,
+                         void* stream, tb200_handle_t* out) {
+    TB_TRY(check_factorize_args(kind, dtype, m, n, vc_host, vr_host, true));
+    const size_t esz = dt_size(dtype);
+    const int64_t nvc = (kind == TB200_HANKEL) ? m + n - 1 : (kind == TB200_TOEPLITZ ? m : n);
+    const int64_t nvr = (kind == TB200_TOEPLITZ) ? n : 0;
+    std::shared_ptr<DevBuf> dvc, dvr;
+    cudaStream_t s = (cudaStream_t)stream;
+    TB_TRY(dev_alloc(dvc, (size_t)nvc * esz, "vc staging"));
+    TB_CUDA(cudaMemcpyAsync(dvc->p, vc_host, (size_t)nvc * esz, cudaMemcpyHostToDevice, s), "vc upload");
+    if (nvr) {
+        TB_TRY(dev_alloc(dvr, (size_t)nvr * esz, "vr staging"));
+        TB_CUDA(cudaMemcpyAsync(dvr->p, vr_host, (size_t)nvr * esz, cudaMemcpyHostToDevice, s), "vr upload");
+    }
+    int st = tb200_factorize(kind, dtype, m, n, dvc->p, nvr ? dvr->p : nullptr, stream, out);
+    TB_CUDA(cudaStreamSynchronize(s), "factorize_host sync");   // staging buffers are freed on return
+    return st;
+}
+
+int tb200_destroy(tb200_handle_t h) {
+    delete h;
+    return TB200_OK;
+}
+
+int tb200_info(tb200_handle_t h, int64_t* m, int64_t* n, int64_t* n_embed, int* dtype, int* kind) {
+    if (!h) return set_error(TB200_BAD_ARG, "handle is NULL");
+    if (m) *m = h->m;
+    if (n) *n = h->n;
+    if (n_embed) *n_embed = h->Np;
+    if (dtype) *dtype = h->dtype;
+    if (kind) *kind = h->kind;
+    return TB200_OK;
+}
+
+int tb200_spectrum_buffer(tb200_handle_t h, void** ptr, int64_t* bytes) {
+    if (!h || !ptr || !bytes) return set_error(TB200_BAD_ARG, "NULL argument");
+    *ptr = h->spec->p;
+    *bytes = (int64_t)h->Np * (h->prec ? 16 : 8);
+    return TB200_OK;
+}
+
+// ---- mul! --------------------------------------------------------------------------------
+static int mul_impl(tb200_fact* h, const void* spec, bool is_ldiv, void* y, int64_t ldy, int ydtype, const void* x,
+                    int64_t ldx, int xdtype, int64_t ncols, const double alpha[2], const double beta[2], cudaStream_t s) {
+    if (!h) return set_error(TB200_BAD_ARG, "handle is NULL");
+    if (!dt_valid(xdtype) || !dt_valid(ydtype)) return set_error(TB200_BAD_ARG, "unknown dtype");
+    if (dt_prec(xdtype) != h->prec || dt_prec(ydtype) != h->prec)
+        return set_error(TB200_BAD_ARG, "vector precision must match the factorization's (%s)", h->prec ? "Float64" : "Float32");
+    if (ncols < 0) return set_error(TB200_BAD_ARG, "negative column count");
+    if (ncols == 0) return TB200_OK;
+    if (!x || !y) return set_error(TB200_BAD_ARG, "x or y is NULL");
+    if (ldx < h->n || ldy < h->m)
+        return set_error(TB200_DIM_MISMATCH, "leading dimensions (%lld, %lld) smaller than the matrix size %lldx%lld",
+                         (long long)ldy, (long long)ldx, (long long)h->m, (long long)h->n);
+    const bool xc = dt_is_cplx(xdtype), yc = dt_is_cplx(ydtype);
+    ConvCall c;
+    c.x = x; c.ldx = ldx; c.n_in = h->n; c.reverse_x = h->reverse_x;
+    c.y = y; c.ldy = ldy; c.m_out = h->m;
+    c.ncols = ncols; c.spec = spec;
+    c.scale = 1.0 / (double)h->Np;
+    c.alpha[0] = alpha ? alpha[0] : 1.0; c.alpha[1] = alpha ? alpha[1] : 0.0;
+    c.beta[0] = beta ? beta[0] : 0.0; c.beta[1] = beta ? beta[1] : 0.0;
+    c.has_beta = (c.beta[0] != 0.0 || c.beta[1] != 0.0);
+    if (!yc) {
+        if (!is_ldiv && (!h->a_real || xc || c.alpha[1] != 0.0 || c.beta[1] != 0.0))
+            return set_error(TB200_BAD_ARG, "a real y requires a real matrix, real x and real alpha/beta (InexactError in the reference)");
+        if (is_ldiv && !h->a_real)
+            return set_error(TB200_BAD_ARG, "real b with a complex Circulant (InexactError in the reference)");
+        c.x_mode = IO_PAIR; c.y_mode = IO_PAIR; c.nfft = (ncols + 1) / 2;
+    } else {
+        c.x_mode = mode_for(xc); c.y_mode = IO_CPLX; c.nfft = ncols;
+    }
+    return run_conv(h, c, s);
+}
+
+int tb200_mul(tb200_handle_t h, void* y, int64_t ldy, int ydtype, const void* x, int64_t ldx, int xdtype, int64_t ncols,
+              const double alpha[2], const double beta[2], void* stream) {
+    if (!h) return set_error(TB200_BAD_ARG, "handle is NULL");
+    return mul_impl(h, h->spec->p, false, y, ldy, ydtype, x, ldx, xdtype, ncols, alpha, beta, (cudaStream_t)stream);
+}
+
+int tb200_mul_host(tb200_handle_t h, void* y_host, int64_t ldy, int ydtype, const void* x_host, int64_t ldx, int xdtype,
+                   int64_t ncols, const double alpha[2], const double beta[2]) {
+    if (!h) return set_error(TB200_BAD_ARG, "handle is NULL");
+    if (!dt_valid(xdtype) || !dt_valid(ydtype)) return set_error(TB200_BAD_ARG, "unknown dtype");
+    if (ncols <= 0) return TB200_OK;
+    if (ldx < h->n || ldy < h->m) return set_error(TB200_DIM_MISMATCH, "leading dimensions smaller than the matrix size");
+    const size_t xsz = dt_size(xdtype), ysz = dt_size(ydtype);
+    const bool has_beta = beta && (beta[0] != 0.0 || beta[1] != 0.0);
+    // column chunks (even, so real columns keep pairing up)
+    int64_t cc = std::max<int64_t>(2, g_host_chunk_bytes.load() / (int64_t)std::max<size_t>(h->n * xsz, h->m * ysz));
+    cc &= ~int64_t(1);
+    cc = std::min<int64_t>(cc, (ncols + 1) & ~int64_t(1));
+    const int NS = 2;
+    std::shared_ptr<DevBuf> xd[NS], yd[NS];
+    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[NS], ev_cmp[NS], ev_out[NS];
+    int st = TB200_OK;
+    for (int i = 0; i < NS; ++i) { ev_in[i] = ev_cmp[i] = ev_out[i] = nullptr; }
+    auto cleanup = [&]() {
+        cudaDeviceSynchronize();
+        for (int i = 0; i < NS; ++i) {
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_cmp[i]) cudaEventDestroy(ev_cmp[i]);
+            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+        }
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_cmp) cudaStreamDestroy(s_cmp);
+        if (s_out) cudaStreamDestroy(s_out);
+    };
+#define TB_HOSTTRY(expr) do { st = (expr); if (st != TB200_OK) { cleanup(); return st; } } while (0)
+    TB_HOSTTRY(cuda_status(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking), "stream"));
+    TB_HOSTTRY(cuda_status(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking), "stream"));
+    TB_HOSTTRY(cuda_status(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking), "stream"));
+    for (int i = 0; i < NS; ++i) {
+        TB_HOSTTRY(dev_alloc(xd[i], (size_t)cc * h->n * xsz, "host-path x buffer"));
+        TB_HOSTTRY(dev_alloc(yd[i], (size_t)cc * h->m * ysz, "host-path y buffer"));
+        TB_HOSTTRY(cuda_status(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming), "event"));
+        TB_HOSTTRY(cuda_status(cudaEventCreateWithFlags(&ev_cmp[i], cudaEventDisableTiming), "event"));
+        TB_HOSTTRY(cuda_status(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming), "event"));
+    }
+    int64_t chunk = 0;
+    for (int64_t c0 = 0; c0 < ncols; c0 += cc, ++chunk) {
+        const int sl = (int)(chunk % NS);
+        const int64_t nc = std::min(cc, ncols - c0);
+        const char* xs = reinterpret_cast<const char*>(x_host) + (size_t)c0 * ldx * xsz;
+        char* ys = reinterpret_cast<char*>(y_host) + (size_t)c0 * ldy * ysz;
+        // H2D (x buffer free once the previous compute on this slot is done; y buffer once drained)
+        if (chunk >= NS) {
+            TB_HOSTTRY(cuda_status(cudaStreamWaitEvent(s_in, ev_cmp[sl], 0), "wait"));
+            TB_HOSTTRY(cuda_status(cudaStreamWaitEvent(s_in, ev_out[sl], 0), "wait"));
+        }
+        TB_HOSTTRY(cuda_status(cudaMemcpy2DAsync(xd[sl]->p, (size_t)h->n * xsz, xs, (size_t)ldx * xsz, (size_t)h->n * xsz,
+                                                 (size_t)nc, cudaMemcpyHostToDevice, s_in), "x upload"));
+        if (has_beta)
+            TB_HOSTTRY(cuda_status(cudaMemcpy2DAsync(yd[sl]->p, (size_t)h->m * ysz, ys, (size_t)ldy * ysz, (size_t)h->m * ysz,
+                                                     (size_t)nc, cudaMemcpyHostToDevice, s_in), "y upload"));
+        TB_HOSTTRY(cuda_status(cudaEventRecord(ev_in[sl], s_in), "record"));
+        // compute
+        TB_HOSTTRY(cuda_status(cudaStreamWaitEvent(s_cmp, ev_in[sl], 0), "wait"));
+        TB_HOSTTRY(mul_impl(h, h->spec->p, false, yd[sl]->p, h->m, ydtype, xd[sl]->p, h->n, xdtype, nc, alpha, beta, s_cmp));
+        TB_HOSTTRY(cuda_status(cudaEventRecord(ev_cmp[sl], s_cmp), "record"));
+        // D2H
+        TB_HOSTTRY(cuda_status(cudaStreamWaitEvent(s_out, ev_cmp[sl], 0), "wait"));
+        TB_HOSTTRY(cuda_status(cudaMemcpy2DAsync(ys, (size_t)ldy * ysz, yd[sl]->p, (size_t)h->m * ysz, (size_t)h->m * ysz,
+                                                 (size_t)nc, cudaMemcpyDeviceToHost, s_out), "y download"));
+        TB_HOSTTRY(cuda_status(cudaEventRecord(ev_out[sl], s_out), "record"));
+    }
+    TB_HOSTTRY(cuda_status(cudaStreamSynchronize(s_out), "host-path sync"));
+#undef TB_HOSTTRY
+    cleanup();
+    return TB200_OK;
+}
+
+int tb200_mul_direct(int kind, int dtype, int64_t m, int64_t n, const void* vc, const void* vr, void* y, int64_t ldy,
+                     int ydtype, const void* x, int64_t ldx, int xdtype, int64_t ncols, const double alpha[2],
+                     const double beta[2], void* stream) {
+    TB_TRY(check_factorize_args(kind, dtype, m, n, vc, vr, true));
+    if (!dt_valid(xdtype) || !dt_valid(ydtype)) return set_error(TB200_BAD_ARG, "unknown dtype");
+    const int prec = dt_prec(dtype);
+    if (dt_prec(xdtype) != prec || dt_prec(ydtype) != prec) return set_error(TB200_BAD_ARG, "precision mismatch");
+    if (ncols <= 0) return TB200_OK;
+    if (ldx < n || ldy < m) return set_error(TB200_DIM_MISMATCH, "leading dimensions smaller than the matrix size");
+    const double a0 = alpha ? alpha[0] : 1.0, a1 = alpha ? alpha[1] : 0.0;
+    const double b0 = beta ? beta[0] : 0.0, b1 = beta ? beta[1] : 0.0;
+    const int has_beta = (b0 != 0.0 || b1 != 0.0);
+    if (!dt_is_cplx(ydtype) && (dt_is_cplx(dtype) || dt_is_cplx(xdtype) || a1 != 0.0 || b1 != 0.0))
+        return set_error(TB200_BAD_ARG, "a real y requires a real matrix, real x and real alpha/beta");
+    dim3 grid((unsigned)((m + 127) / 128), (unsigned)ncols);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (prec)
+        k_direct_mul<double><<<grid, 128, 0, s>>>(y, ldy, dt_is_cplx(ydtype), x, ldx, dt_is_cplx(xdtype), kind, vc, vr,
+                                                  dt_is_cplx(dtype), m, n, mk<double>(a0, a1), mk<double>(b0, b1), has_beta);
+    else
+        k_direct_mul<float><<<grid, 128, 0, s>>>(y, ldy, dt_is_cplx(ydtype), x, ldx, dt_is_cplx(xdtype), kind, vc, vr,
+                                                 dt_is_cplx(dtype), m, n, mk<float>((float)a0, (float)a1),
+                                                 mk<float>((float)b0, (float)b1), has_beta);
+    count_launch();
+    return cuda_status(cudaGetLastError(), "k_direct_mul");
+}
+
+// ---- Circulant family ------------------------------------------------------------------------
+static int require_circulant(tb200_fact* h) {
+    if (!h) return set_error(TB200_BAD_ARG, "handle is NULL");
+    if (h->kind != TB200_CIRCULANT) return set_error(TB200_BAD_ARG, "operation is only defined for Circulant factorizations");
+    return TB200_OK;
+}
+
+static int spec_map_launch(tb200_fact* h, void* out, const void* in, int op, double tol, cudaStream_t s) {
+    if (h->prec) k_spec_map<double><<<ew_grid(h->Np), 256, 0, s>>>((cx<double>*)out, (const cx<double>*)in, h->Np, op, tol);
+    else k_spec_map<float><<<ew_grid(h->Np), 256, 0, s>>>((cx<float>*)out, (const cx<float>*)in, h->Np, op, (float)tol);
+    count_launch();
+    return cuda_status(cudaGetLastError(), "k_spec_map");
+}
+
+static int ensure_inv_spec(tb200_fact* h, cudaStream_t s) {
+    if (h->inv_spec) return TB200_OK;
+    std::shared_ptr<DevBuf> b;
+    TB_TRY(dev_alloc(b, (size_t)h->Np * (h->prec ? 16 : 8), "reciprocal spectrum"));
+    TB_TRY(spec_map_launch(h, b->p, h->spec->p, OP_INV, 0.0, s));
+    h->inv_spec = b;
+    return TB200_OK;
+}
+
+int tb200_circ_ldiv(tb200_handle_t h, void* x, int64_t ldx, const void* b, int64_t ldb, int dtype, int64_t ncols,
+                    void* stream) {
+    TB_TRY(require_circulant(h));
+    TB_TRY(ensure_inv_spec(h, (cudaStream_t)stream));
+    const double one[2] = {1, 0}, zero[2] = {0, 0};
+    // tmp ./= vcvr_dft is applied as a multiply by the cached reciprocal spectrum
+    return mul_impl(h, h->inv_spec->p, true, x, ldx, dtype, b, ldb, dtype, ncols, one, zero, (cudaStream_t)stream);
+}
+
+int tb200_circ_spectrum(tb200_handle_t h, void* out, void* stream) {
+    TB_TRY(require_circulant(h));
+    if (!out) return set_error(TB200_BAD_ARG, "out is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int l1 = h->two_level ? h->log2l1 : 0;
+    if (h->prec) k_unscramble<double><<<ew_grid(h->Np), 256, 0, s>>>((cx<double>*)out, (const cx<double>*)h->spec->p, h->Np, l1, h->log2l2);
+    else k_unscramble<float><<<ew_grid(h->Np), 256, 0, s>>>((cx<float>*)out, (const cx<float>*)h->spec->p, h->Np, l1, h->log2l2);
+    count_launch();
+    return cuda_status(cudaGetLastError(), "k_unscramble");
+}
+
+static int clone_plan(tb200_fact* h, tb200_fact** out) {
+    tb200_fact* g = nullptr;
+    TB_TRY(new_handle(h->kind, h->dtype, h->m, h->n, &g));
+    *out = g;
+    return TB200_OK;
+}
+
+int tb200_circ_map(tb200_handle_t h, int op, double tol, void* stream, tb200_handle_t* out) {
+    TB_TRY(require_circulant(h));
+    if (!out) return set_error(TB200_BAD_ARG, "out is NULL");
+    if (op < 0 || op > 4) return set_error(TB200_BAD_ARG, "unknown spectrum op %d", op);
+    tb200_fact* g = nullptr;
+    TB_TRY(clone_plan(h, &g));
+    int st = spec_map_launch(h, g->spec->p, h->spec->p, op, tol, (cudaStream_t)stream);
+    if (st != TB200_OK) { delete g; return st; }
+    // sqrt/inv/pinv/conj of a real circulant's spectrum stay Hermitian only for inv/pinv/conj; sqrt of a
+    // spectrum with negative real eigenvalues does not, but the reference takes maybereal anyway (:314).
+    g->spec_valid = true;
+    *out = g;
+    return TB200_OK;
+}
+
+int tb200_circ_mul(tb200_handle_t a, tb200_handle_t b, void* stream, tb200_handle_t* out) {
+    TB_TRY(require_circulant(a));
+    TB_TRY(require_circulant(b));
+    if (!out) return set_error(TB200_BAD_ARG, "out is NULL");
+    if (a->n != b->n)
+        return set_error(TB200_DIM_MISMATCH, "size of matrix A, %lldx%lld, does not match size of matrix B, %lldx%lld",
+                         (long long)a->n, (long long)a->n, (long long)b->n, (long long)b->n);
+    if (a->prec != b->prec) return set_error(TB200_BAD_ARG, "precision mismatch between the two factorizations");
+    tb200_fact* g = nullptr;
+    const int dt = (dt_is_cplx(a->dtype) || dt_is_cplx(b->dtype)) ? (a->prec ? TB200_C64 : TB200_C32) : a->dtype;
+    TB_TRY(new_handle(TB200_CIRCULANT, dt, a->n, a->n, &g));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (a->prec) k_spec_mul<double><<<ew_grid(a->Np), 256, 0, s>>>((cx<double>*)g->spec->p, (const cx<double>*)a->spec->p, (const cx<double>*)b->spec->p, a->Np);
+    else k_spec_mul<float><<<ew_grid(a->Np), 256, 0, s>>>((cx<float>*)g->spec->p, (const cx<float>*)a->spec->p, (const cx<float>*)b->spec->p, a->Np);
+    count_launch();
+    int st = cuda_status(cudaGetLastError(), "k_spec_mul");
+    if (st != TB200_OK) { delete g; return st; }
+    g->spec_valid = true;
+    *out = g;
+    return TB200_OK;
+}
+
+int tb200_circ_to_vc(tb200_handle_t h, void* vc_out, int out_dtype, void* stream) {
+    TB_TRY(require_circulant(h));
+    if (!vc_out) return set_error(TB200_BAD_ARG, "vc_out is NULL");
+    if (!dt_valid(out_dtype) || dt_prec(out_dtype) != h->prec) return set_error(TB200_BAD_ARG, "output dtype must have the factorization's precision");
+    ConvCall c;
+    c.x = h->spec->p; c.ldx = h->Np; c.x_mode = IO_SPEC; c.n_in = h->Np;
+    c.y = vc_out; c.ldy = h->Np; c.y_mode = dt_is_cplx(out_dtype) ? IO_CPLX : IO_REAL; c.m_out = h->n;
+    c.ncols = 1; c.nfft = 1; c.do_fwd = 0; c.do_inv = 1; c.spec = nullptr;
+    c.scale = 1.0 / (double)h->Np;
+    return run_conv(h, c, (cudaStream_t)stream);
+}
+
+int tb200_precond_vector(int which, int kind, int dtype, int64_t n, const void* vc, const void* vr, void* v_out,
+                         void* stream) {
+    TB_TRY(check_factorize_args(kind, dtype, n, n, vc, vr, true));
+    if (kind == TB200_HANKEL) return set_error(TB200_BAD_ARG, "strang/chan are defined for Toeplitz-structured matrices");
+    if (which != 0 && which != 1) return set_error(TB200_BAD_ARG, "which must be 0 (strang) or 1 (chan)");
+    if (!v_out) return set_error(TB200_BAD_ARG, "v_out is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dt_prec(dtype)) k_strang_chan<double><<<ew_grid(n), 256, 0, s>>>(v_out, which, kind, vc, vr, dt_is_cplx(dtype), n);
+    else k_strang_chan<float><<<ew_grid(n), 256, 0, s>>>(v_out, which, kind, vc, vr, dt_is_cplx(dtype), n);
+    count_launch();
+    return cuda_status(cudaGetLastError(), "k_strang_chan");
+}
+
+// ---- Levinson / Durbin -----------------------------------------------------------------------
+int tb200_levinson_batched(int dtype, int64_t n, int64_t nsys, const void* r, int64_t ldr, const void* b, int64_t ldb,
+                           void* x, int64_t ldx, const void* diag, void* stream) {
+    if (n <= 0 || nsys < 0) return set_error(TB200_BAD_ARG, "bad sizes");
+    if (nsys == 0) return TB200_OK;
+    if (!b || !x || (n > 1 && !r)) return set_error(TB200_BAD_ARG, "NULL argument");
+    if (ldb < n || ldx < n || (n > 1 && ldr < n - 1))
+        return set_error(TB200_DIM_MISMATCH, "length(x) = %lld / length(b) = %lld != %lld = length(r) + 1", (long long)ldx, (long long)ldb, (long long)n);
+    return levinson_dispatch(dtype, false, n, nsys, r, ldr, b, ldb, x, ldx, diag, (cudaStream_t)stream);
+}
+
+int tb200_durbin_batched(int dtype, int64_t n, int64_t nsys, const void* r, int64_t ldr, void* y, int64_t ldy, void* stream) {
+    if (n <= 0 || nsys < 0) return set_error(TB200_BAD_ARG, "bad sizes");
+    if (nsys == 0) return TB200_OK;
+    if (!r || !y) return set_error(TB200_BAD_ARG, "NULL argument");
+    if (ldr < n || ldy < n) return set_error(TB200_DIM_MISMATCH, "length(y) = %lld != %lld = length(r)", (long long)ldy, (long long)n);
+    return levinson_dispatch(dtype, true, n, nsys, r, ldr, nullptr, 0, y, ldy, nullptr, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// iterative solvers
+// ---------------------------------------------------------------------------------------
+namespace tb {
+
+typedef std::complex<double> zc;
+
+template <typename T>
+struct KrylovCtx {
+    tb200_fact* A; tb200_fact* M; int dtype; int64_t n; cudaStream_t s;
+    std::shared_ptr<DevBuf> partials, counter, out;
+    double host_out[4];
+
+    int init() {
+        TB_TRY(dev_alloc(partials, sizeof(double) * 4 * 4096, "dot partials"));
+        TB_TRY(dev_alloc(counter, 16, "dot counter"));
+        TB_TRY(dev_alloc(out, sizeof(double) * 4, "dot result"));
+        TB_CUDA(cudaMemsetAsync(counter->p, 0, 16, s), "memset");
+        return TB200_OK;
+    }
+    // host_out[0..1] = dot(a1,b1), [2..3] = dot(a2,b2); synchronises the stream
+    int dots(const T* a1, const T* b1, const T* a2, const T* b2) {
+        unsigned grid = std::min<unsigned>(ew_grid(n), 4096u);
+        k_dot2<T><<<grid, 256, 0, s>>>(a1, b1, a2, b2, n, (double*)partials->p, (unsigned*)counter->p, (double*)out->p);
+        count_launch();
+        TB_CUDA(cudaGetLastError(), "k_dot2");
+        TB_CUDA(cudaMemcpyAsync(host_out, out->p, sizeof(double) * 4, cudaMemcpyDeviceToHost, s), "dot readback");
+        TB_CUDA(cudaStreamSynchronize(s), "dot sync");
+        return TB200_OK;
+    }
+    int mulA(T* y, const T* x, zc alpha, zc beta) {
+        const double a[2] = {alpha.real(), alpha.imag()}, b[2] = {beta.real(), beta.imag()};
+        return mul_impl_fwd(y, x, a, b);
+    }
+    int mul_impl_fwd(T* y, const T* x, const double a[2], const double b[2]);
+    int precond(T* out_v, const T* in_v);   // out = M \ in (may alias)
+};
+
+}  // namespace tb
+
+// mul_impl / tb200_circ_ldiv live in the extern "C" block above; thin forwarders:
+template <typename T>
+int tb::KrylovCtx<T>::mul_impl_fwd(T* y, const T* x, const double a[2], const double b[2]) {
+    return tb200_mul(A, y, n, dtype, x, n, dtype, 1, a, b, (void*)s);
+}
+template <typename T>
+int tb::KrylovCtx<T>::precond(T* out_v, const T* in_v) {
+    if (!M) {
+        if (out_v != in_v) TB_CUDA(cudaMemcpyAsync(out_v, in_v, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, s), "copy");
+        return TB200_OK;
+    }
+    return tb200_circ_ldiv(M, out_v, n, in_v, n, dtype, 1, (void*)s);
+}
+
+namespace tb {
+
+static int check_krylov(tb200_fact* A, tb200_fact* M, int dtype, int64_t n, const void* x, const void* b) {
+    if (!A) return set_error(TB200_BAD_ARG, "A is NULL");
+    if (!x || !b) return set_error(TB200_BAD_ARG, "x or b is NULL");
+    if (!dt_valid(dtype) || dt_prec(dtype) != A->prec) return set_error(TB200_BAD_ARG, "vector precision must match A");
+    if (A->m != A->n || A->n != n) return set_error(TB200_DIM_MISMATCH, "A is %lldx%lld but the vectors have length %lld", (long long)A->m, (long long)A->n, (long long)n);
+    if (!dt_is_cplx(dtype) && !A->a_real) return set_error(TB200_BAD_ARG, "real vectors with a complex matrix");
+    if (M) {
+        if (M->kind != TB200_CIRCULANT || M->n != n) return set_error(TB200_DIM_MISMATCH, "preconditioner must be a Circulant factorization of size %lld", (long long)n);
+        if (M->prec != A->prec) return set_error(TB200_BAD_ARG, "preconditioner precision mismatch");
+        if (!dt_is_cplx(dtype) && !M->a_real) return set_error(TB200_BAD_ARG, "real vectors with a complex preconditioner");
+    }
+    return TB200_OK;
+}
+
+// IterativeLinearSolvers.cgs, src/iterativeLinearSolvers.jl:99-215
+template <typename T>
+static int cgs_t(tb200_fact* A, tb200_fact* M, T* x, const T* b, int dtype, int64_t n, int max_it, double tol,
+                 double* err_out, int* iter_out, int* flag_out, cudaStream_t s) {
+    KrylovCtx<T> k{A, M, dtype, n, s};
+    TB_TRY(k.init());
+    std::shared_ptr<DevBuf> buf;
+    TB_TRY(dev_alloc(buf, sizeof(T) * (size_t)n * 8, "cgs work vectors"));
+    T* u = (T*)buf->p; T* p = u + n; T* ph = p + n; T* q = ph + n; T* uh = q + n; T* vh = uh + n; T* r = vh + n; T* rt = r + n;
+    TB_CUDA(cudaMemsetAsync(buf->p, 0, sizeof(T) * (size_t)n * 6, s), "memset");       // u,p,ph,q,uh,vh = zeros (:141-146)
+    const unsigned grid = ew_grid(n);
+    int iter = 0, flag = 0;
+    TB_TRY(k.dots(b, b, nullptr, nullptr));
+    double bnrm2 = std::sqrt(k.host_out[0]);                                            // :136
+    if (bnrm2 == 0) bnrm2 = 1.0;
+    TB_CUDA(cudaMemcpyAsync(r, b, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, s), "copy");   // :149
+    TB_TRY(k.mulA(r, x, zc(-1, 0), zc(1, 0)));                                          // :150
+    TB_TRY(k.dots(r, r, nullptr, nullptr));
+    double error = std::sqrt(k.host_out[0]) / bnrm2;                                    // :152
+    zc rho(0, 0), rho1(0, 0);
+    if (error < tol) { *err_out = error; *iter_out = 0; *flag_out = 0; return TB200_OK; }   // :154-156
+    TB_CUDA(cudaMemcpyAsync(rt, r, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, s), "copy");  // :158
+    TB_TRY(k.dots(rt, r, nullptr, nullptr));
+    zc rho_next(k.host_out[0], k.host_out[1]);
+    for (int it = 1; it <= max_it; ++it) {
+        iter = it;
+        rho = rho_next;                                                                 // :163
+        if (rho == zc(0, 0)) break;                                                     // :164-166
+        zc beta(0, 0);
+        if (it > 1) beta = rho / rho1;                                                  // :169
+        k_cgs_dir<T><<<grid, 256, 0, s>>>(u, p, r, q, make_double2(beta.real(), beta.imag()), it == 1, n);   // :168-177
+        count_launch();
+        TB_TRY(k.precond(ph, p));                                                       // :179-180
+        TB_TRY(k.mulA(vh, ph, zc(1, 0), zc(0, 0)));                                     // :182
+        TB_TRY(k.dots(rt, vh, nullptr, nullptr));
+        const zc alpha = rho / zc(k.host_out[0], k.host_out[1]);                        // :184
+        k_cgs_q<T><<<grid, 256, 0, s>>>(q, uh, u, vh, make_double2(alpha.real(), alpha.imag()), n);          // :185-188
+        count_launch();
+        TB_TRY(k.precond(uh, uh));                                                      // :189
+        k_axpy<T><<<grid, 256, 0, s>>>(x, make_double2(alpha.real(), alpha.imag()), uh, n);                  // :192-194
+        count_launch();
+        TB_TRY(k.mulA(r, uh, -alpha, zc(1, 0)));                                        // :196
+        TB_TRY(k.dots(r, r, rt, r));                                                    // norm(r) and the next rho in one sweep
+        error = std::sqrt(k.host_out[0]) / bnrm2;                                       // :198
+        rho_next = zc(k.host_out[2], k.host_out[3]);
+        if (error <= tol) break;                                                        // :199-201
+        rho1 = rho;
+    }
+    if (error <= tol) flag = 0;
+    else if (rho == zc(0, 0)) flag = -1;
+    else flag = 1;
+    *err_out = error; *iter_out = iter; *flag_out = flag;
+    TB_CUDA(cudaStreamSynchronize(s), "cgs sync");
+    return TB200_OK;
+}
+
+// IterativeLinearSolvers.cg, src/iterativeLinearSolvers.jl:9-97.  flag_out = 2 marks the
+// reference's value-less early return (:57-59); the host layer turns it into the same failure.
+template <typename T>
+static int cg_t(tb200_fact* A, tb200_fact* M, T* x, const T* b, int dtype, int64_t n, int max_it, double tol,
+                double* err_out, int* iter_out, int* flag_out, cudaStream_t s) {
+    KrylovCtx<T> k{A, M, dtype, n, s};
+    TB_TRY(k.init());
+    std::shared_ptr<DevBuf> buf;
+    TB_TRY(dev_alloc(buf, sizeof(T) * (size_t)n * 4, "cg work vectors"));
+    T* z = (T*)buf->p; T* q = z + n; T* p = q + n; T* r = p + n;
+    TB_CUDA(cudaMemsetAsync(buf->p, 0, sizeof(T) * (size_t)n * 3, s), "memset");
+    const unsigned grid = ew_grid(n);
+    int iter = 0, flag = 0;
+    TB_TRY(k.dots(b, b, nullptr, nullptr));
+    double bnrm2 = std::sqrt(k.host_out[0]);
+    if (bnrm2 == 0.0) bnrm2 = 1.0;
+    TB_CUDA(cudaMemcpyAsync(r, b, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, s), "copy");
+    TB_TRY(k.mulA(r, x, zc(-1, 0), zc(1, 0)));                                          // :55  r = b - A*x
+    TB_TRY(k.dots(r, r, nullptr, nullptr));
+    double error = std::sqrt(k.host_out[0]) / bnrm2;
+    if (error < tol) { *err_out = error; *iter_out = 0; *flag_out = 2; return TB200_OK; }   // :57-59
+    zc rho1(0, 0);
+    for (int it = 1; it <= max_it; ++it) {
+        iter = it;
+        TB_TRY(k.precond(z, r));                                                        // :64-65
+        TB_TRY(k.dots(r, z, nullptr, nullptr));
+        const zc rho(k.host_out[0], k.host_out[1]);                                     // :67
+        zc beta(0, 0);
+        if (it > 1) beta = rho / rho1;
+        k_cg_dir<T><<<grid, 256, 0, s>>>(p, z, make_double2(beta.real(), beta.imag()), it == 1, n);          // :69-76
+        count_launch();
+        TB_TRY(k.mulA(q, p, zc(1, 0), zc(0, 0)));                                       // :79
+        TB_TRY(k.dots(p, q, nullptr, nullptr));
+        const zc alpha = rho / zc(k.host_out[0], k.host_out[1]);                        // :80
+        k_cg_upd<T><<<grid, 256, 0, s>>>(x, r, p, q, make_double2(alpha.real(), alpha.imag()), n);           // :81-84
+        count_launch();
+        TB_TRY(k.dots(r, r, nullptr, nullptr));
+        error = std::sqrt(k.host_out[0]) / bnrm2;                                       // :86
+        if (error <= tol) break;
+        rho1 = rho;
+    }
+    if (error > tol) flag = 1;
+    *err_out = error; *iter_out = iter; *flag_out = flag;
+    TB_CUDA(cudaStreamSynchronize(s), "cg sync");
+    return TB200_OK;
+}
+
+}  // namespace tb
+
+extern "C" {
+
+int tb200_cgs(tb200_handle_t A, tb200_handle_t M, void* x, const void* b, int dtype, int64_t n, int max_it, double tol,
+              double* err, int* iter, int* flag, void* stream) {
+    TB_TRY(check_krylov(A, M, dtype, n, x, b));
+    double e = 0; int it = 0, fl = 0, st;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (dtype) {
+    case TB200_F32: st = cgs_t<float>(A, M, (float*)x, (const float*)b, dtype, n, max_it, tol, &e, &it, &fl, s); break;
+    case TB200_F64: st = cgs_t<double>(A, M, (double*)x, (const double*)b, dtype, n, max_it, tol, &e, &it, &fl, s); break;
+    case TB200_C32: st = cgs_t<float2>(A, M, (float2*)x, (const float2*)b, dtype, n, max_it, tol, &e, &it, &fl, s); break;
+    default: st = cgs_t<double2>(A, M, (double2*)x, (const double2*)b, dtype, n, max_it, tol, &e, &it, &fl, s); break;
+    }
+    if (err) *err = e;
+    if (iter) *iter = it;
+    if (flag) *flag = fl;
+    return st;
+}
+
+int tb200_cg(tb200_handle_t A, tb200_handle_t M, void* x, const void* b, int dtype, int64_t n, int max_it, double tol,
+             double* err, int* iter, int* flag, void* stream) {
+    TB_TRY(check_krylov(A, M, dtype, n, x, b));
+    if (dt_is_cplx(dtype)) return set_error(TB200_BAD_ARG, "cg is defined for real (BlasReal) element types only");
+    double e = 0; int it = 0, fl = 0, st;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == TB200_F32) st = cg_t<float>(A, M, (float*)x, (const float*)b, dtype, n, max_it, tol, &e, &it, &fl, s);
+    else st = cg_t<double>(A, M, (double*)x, (const double*)b, dtype, n, max_it, tol, &e, &it, &fl, s);
+    if (err) *err = e;
+    if (iter) *iter = it;
+    if (flag) *flag = fl;
+    return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,277 @@
+// Shared-memory radix-16 FFT building blocks for sm_100a (hand-written; no cuFFT).
+//
+// Design: an L-point complex FFT (L = 2^LOG2L) is done by NT = L/16 threads, 16
+// points per thread in registers.  Forward transforms are decimation-in-frequency
+// (natural order in -> digit-reversed order out), inverse transforms are the exact
+// mirror (decimation-in-time, digit-reversed in -> natural out), so a
+// forward -> pointwise spectrum multiply -> inverse chain needs no re-ordering pass
+// at all and the multiply happens in registers between the two halves.  This is
+// what replaces the reference's `mul!(tmp, dft, tmp); tmp .*= vcvr_dft; dft \ tmp`
+// (/root/reference/src/linearalgebra.jl:63-67).
+//
+// Shared memory is used in place (a thread reads and writes the same 16 slots in a
+// stage), one __syncthreads per stage, with an XOR swizzle that makes every stage
+// bank-conflict free for 16-byte (complex<double>) and 8-byte (complex<float>)
+// elements (verified by brute force over all stages).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tb {
+
+constexpr int LOGE = 4;          // 16 points per thread
+constexpr int E = 1 << LOGE;
+constexpr int LOG2TWN = 14;      // twiddle table length (max single-pass FFT: 16384)
+constexpr int TWN = 1 << LOG2TWN;
+
+template <typename R> struct CxT;
+template <> struct CxT<float> { using type = float2; };
+template <> struct CxT<double> { using type = double2; };
+template <typename R> using cx = typename CxT<R>::type;
+
+template <typename R> __host__ __device__ __forceinline__ cx<R> mk(R a, R b) { cx<R> r; r.x = a; r.y = b; return r; }
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+// a*b
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+    C r;
+    r.x = fma(a.x, b.x, -(a.y * b.y));
+    r.y = fma(a.x, b.y, a.y * b.x);
+    return r;
+}
+// a*conj(b)
+template <typename C> __device__ __forceinline__ C cmulc(C a, C b) {
+    C r;
+    r.x = fma(a.x, b.x, a.y * b.y);
+    r.y = fma(a.y, b.x, -(a.x * b.y));
+    return r;
+}
+
+__host__ __device__ constexpr int brev(int x, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((x >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+__host__ __device__ constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
+
+// d * exp(-/+ 2 pi i k/16); k is a compile-time constant after unrolling.
+template <typename R, bool INV>
+__device__ __forceinline__ cx<R> mul_w16(cx<R> d, int k) {
+    const R C1 = (R)0.92387953251128675613, S1 = (R)0.38268343236508977173;
+    const R C2 = (R)0.70710678118654752440;
+    switch (k) {
+    case 0: return d;
+    case 4: return INV ? mk<R>(-d.y, d.x) : mk<R>(d.y, -d.x);
+    case 2: return INV ? mk<R>((d.x - d.y) * C2, (d.x + d.y) * C2) : mk<R>((d.x + d.y) * C2, (d.y - d.x) * C2);
+    case 6: return INV ? mk<R>(-(d.x + d.y) * C2, (d.x - d.y) * C2) : mk<R>((d.y - d.x) * C2, -(d.x + d.y) * C2);
+    default: {
+        R wr = (k == 1) ? C1 : (k == 3) ? S1 : (k == 5) ? -S1 : -C1;
+        R ws = (k == 1 || k == 7) ? S1 : C1;     // sin(2 pi k/16) > 0 for k in 1..7
+        R wi = INV ? ws : -ws;
+        return mk<R>(fma(d.x, wr, -(d.y * wi)), fma(d.x, wi, d.y * wr));
+    }
+    }
+}
+
+// In-register radix-RAD DIF butterfly: natural in -> a[brev(c)] = X[c].
+template <typename R, int RAD>
+__device__ __forceinline__ void dif_regs(cx<R>* a) {
+#pragma unroll
+    for (int h = RAD / 2; h >= 1; h >>= 1) {
+#pragma unroll
+        for (int blk = 0; blk < RAD; blk += 2 * h) {
+#pragma unroll
+            for (int i = 0; i < h; ++i) {
+                cx<R> u = a[blk + i], v = a[blk + i + h];
+                a[blk + i] = cadd(u, v);
+                a[blk + i + h] = mul_w16<R, false>(csub(u, v), i * (8 / h));
+            }
+        }
+    }
+}
+// Mirror: a[brev(c)] = X[c] in -> natural out, conjugate twiddles (unnormalised inverse).
+template <typename R, int RAD>
+__device__ __forceinline__ void dit_regs(cx<R>* a) {
+#pragma unroll
+    for (int h = 1; h <= RAD / 2; h <<= 1) {
+#pragma unroll
+        for (int blk = 0; blk < RAD; blk += 2 * h) {
+#pragma unroll
+            for (int i = 0; i < h; ++i) {
+                cx<R> u = a[blk + i], v = mul_w16<R, true>(a[blk + i + h], i * (8 / h));
+                a[blk + i] = cadd(u, v);
+                a[blk + i + h] = csub(u, v);
+            }
+        }
+    }
+}
+
+// Bank-conflict-free swizzles for the contiguous ("row") layout.
+template <typename R> __device__ __forceinline__ int swz(int i);
+template <> __device__ __forceinline__ int swz<double>(int i) { return i ^ (((i >> 3) ^ (i >> 4)) & 7); }
+template <> __device__ __forceinline__ int swz<float>(int i) { return i ^ ((i >> 4) & 15); }
+
+template <typename R> struct RowMap {       // one FFT contiguous in shared memory
+    __device__ __forceinline__ int operator()(int i) const { return swz<R>(i); }
+};
+template <int TA> struct ColMap {           // TA FFTs interleaved element-wise
+    int q;
+    __device__ __forceinline__ int operator()(int i) const { return i * TA + q; }
+};
+
+template <typename R> __device__ __forceinline__ cx<R> ldg_cx(const cx<R>* p) { return __ldg(p); }
+
+// One L-point FFT held by NT threads (t = 0..NT-1), 16 registers each.
+template <typename R, int LOG2L>
+struct SlotFFT {
+    static_assert(LOG2L >= LOGE, "FFT shorter than the per-thread radix");
+    static constexpr int L = 1 << LOG2L;
+    static constexpr int NT = L / E;
+    static constexpr int NFULL = LOG2L / LOGE;
+    static constexpr int REM = LOG2L % LOGE;
+    static constexpr int RR = 1 << REM;
+
+    // position (in the digit-reversed output order) of register i of thread t
+    __host__ __device__ static constexpr int pos_of_reg(int i, int t) {
+        return REM == 0 ? t * E + brev(i, LOGE)
+                        : (t + (i / RR) * NT) * RR + brev(i % RR, REM);
+    }
+    // frequency index held at position P
+    __host__ __device__ static constexpr int freq_of_pos(int P) {
+        int k = 0, mult = 1;
+        for (int s = 0; s < NFULL; ++s) {
+            k += ((P >> (LOG2L - LOGE * (s + 1))) & (E - 1)) * mult;
+            mult <<= LOGE;
+        }
+        if (REM > 0) k += (P & (RR - 1)) * mult;
+        return k;
+    }
+
+    // On entry a[c] = x[t + c*NT].  On exit register i holds X[freq_of_pos(pos_of_reg(i,t))].
+    template <class Map>
+    __device__ __forceinline__ static void forward(cx<R>* a, int t, cx<R>* sm, Map map,
+                                                   const cx<R>* __restrict__ tw) {
+#pragma unroll
+        for (int k = 0; k < NFULL; ++k) {
+            const int ls = LOG2L - LOGE * (k + 1);       // log2 of the stride
+            const int s = 1 << ls;
+            const int g = t >> ls, r = t & (s - 1);
+            const int base = (g << (ls + LOGE)) + r;
+            if (k > 0) {
+#pragma unroll
+                for (int c = 0; c < E; ++c) a[c] = sm[map(base + c * s)];
+            }
+            dif_regs<R, E>(a);
+            if (ls > 0) {
+#pragma unroll
+                for (int c = 1; c < E; ++c) {
+                    cx<R> w = ldg_cx<R>(tw + ((r * c) << (LOG2TWN - LOGE - ls)));
+                    a[brev(c, LOGE)] = cmul(a[brev(c, LOGE)], w);
+                }
+            }
+            const bool last = (k == NFULL - 1) && (REM == 0);
+            if (!last) {
+#pragma unroll
+                for (int c = 0; c < E; ++c) sm[map(base + c * s)] = a[brev(c, LOGE)];
+                __syncthreads();
+            }
+        }
+        if (REM > 0) {
+#pragma unroll
+            for (int u = 0; u < E / RR; ++u) {
+                const int b = t + u * NT;
+#pragma unroll
+                for (int c = 0; c < RR; ++c) a[u * RR + c] = sm[map(b * RR + c)];
+            }
+#pragma unroll
+            for (int u = 0; u < E / RR; ++u) dif_regs<R, RR>(a + u * RR);
+        }
+    }
+
+    // Mirror of forward().  On exit a[j] = y[t + j*NT] (unnormalised).
+    template <class Map>
+    __device__ __forceinline__ static void inverse(cx<R>* a, int t, cx<R>* sm, Map map,
+                                                   const cx<R>* __restrict__ tw) {
+        if (REM > 0) {
+#pragma unroll
+            for (int u = 0; u < E / RR; ++u) dit_regs<R, RR>(a + u * RR);
+#pragma unroll
+            for (int u = 0; u < E / RR; ++u) {
+                const int b = t + u * NT;
+#pragma unroll
+                for (int c = 0; c < RR; ++c) sm[map(b * RR + c)] = a[u * RR + c];
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int k = NFULL - 1; k >= 0; --k) {
+            const int ls = LOG2L - LOGE * (k + 1);
+            const int s = 1 << ls;
+            const int g = t >> ls, r = t & (s - 1);
+            const int base = (g << (ls + LOGE)) + r;
+            const bool first = (k == NFULL - 1) && (REM == 0);
+            if (!first) {
+#pragma unroll
+                for (int c = 0; c < E; ++c) a[brev(c, LOGE)] = sm[map(base + c * s)];
+            }
+            if (ls > 0) {
+#pragma unroll
+                for (int c = 1; c < E; ++c) {
+                    cx<R> w = ldg_cx<R>(tw + ((r * c) << (LOG2TWN - LOGE - ls)));
+                    a[brev(c, LOGE)] = cmulc(a[brev(c, LOGE)], w);
+                }
+            }
+            dit_regs<R, E>(a);
+            if (k > 0) {
+#pragma unroll
+                for (int c = 0; c < E; ++c) sm[map(base + c * s)] = a[c];
+                __syncthreads();
+            }
+        }
+    }
+};
+
+// Runtime versions of the layout maps (for the un-scramble kernel and the host).
+struct PlanDims {
+    int log2l;   // FFT length of this level
+    __host__ __device__ int L() const { return 1 << log2l; }
+    __host__ __device__ int NT() const { return (1 << log2l) / E; }
+    __host__ __device__ int nfull() const { return log2l / LOGE; }
+    __host__ __device__ int rem() const { return log2l % LOGE; }
+    __host__ __device__ int pos_of_reg(int i, int t) const {
+        int rm = rem(), rr = 1 << rm;
+        return rm == 0 ? t * E + brev(i, LOGE) : (t + (i / rr) * NT()) * rr + brev(i % rr, rm);
+    }
+    __host__ __device__ int freq_of_pos(int P) const {
+        int k = 0, mult = 1;
+        for (int s = 0; s < nfull(); ++s) {
+            k += ((P >> (log2l - LOGE * (s + 1))) & (E - 1)) * mult;
+            mult <<= LOGE;
+        }
+        if (rem() > 0) k += (P & ((1 << rem()) - 1)) * mult;
+        return k;
+    }
+    // inverse maps
+    __host__ __device__ int pos_of_freq(int k) const {
+        int P = 0;
+        for (int s = 0; s < nfull(); ++s) {
+            P |= (k & (E - 1)) << (log2l - LOGE * (s + 1));
+            k >>= LOGE;
+        }
+        if (rem() > 0) P |= k & ((1 << rem()) - 1);
+        return P;
+    }
+    // spectrum-layout offset (i*NT + t) of position P
+    __host__ __device__ int layout_of_pos(int P) const {
+        int rm = rem(), rr = 1 << rm, nt = NT();
+        if (rm == 0) {
+            int t = P >> LOGE, c = P & (E - 1);
+            return brev(c, LOGE) * nt + t;
+        }
+        int b = P >> rm, c = P & (rr - 1);
+        int t = b % nt, u = b / nt;
+        return (u * rr + brev(c, rm)) * nt + t;
+    }
+};
+
+}  // namespace tb

@@ -1,0 +1,259 @@
+// Batched Levinson / Durbin recursions (K5): one warp per independent system, the
+// iterates held in registers, reversed operands kept as *shifted* companions so every
+// step is lane-aligned FMAs + one rotate-shuffle per 128 elements + one fused
+// two-value warp reduction.
+//
+// Reference recurrences: /root/reference/src/directLinearSolvers.jl
+//   durbin!  :15-28, levinson! :100-121, reverse_dot :137-145, reverse_increment! :148-168,
+//   levinson(T::SymmetricToeplitz, b) :123-134 (diag normalisation).
+//
+// Layout ("blocked-cyclic", B = 4): element i lives in lane (i/4)%32, register
+// (i/128)*4 + i%4.  With yh[i] = y[k-1-i] and rh[i] = r[k-1-i] (k = current order) the
+// reference's reversed dot / reversed increment become elementwise:
+//   reverse_dot(r_k, x_k) = sum rh[i]*x[i];  x_k += mu*reverse(y_k)  <=>  x[i] += mu*yh[i]
+//   y_k += alpha*reverse(y_k)  <=>  y[i] += alpha*yh[i],  yh <- shift_up(yh + alpha*y_old)
+// and growing the order by one is a shift by one element (register rename inside a block
+// of 4, one rotate shuffle across lanes per 128 elements).
+#include "capi_internal.h"
+
+namespace tb {
+
+constexpr int LB = 4;              // block size of the blocked-cyclic layout
+constexpr int LSPAN = 32 * LB;     // elements per super-row
+
+template <typename R>
+__device__ __forceinline__ R warp_sum(R v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// shift the first SROWS super-rows of v up by one element, inserting `head` at index 0
+template <typename R, int SROWS>
+__device__ __forceinline__ void shift_up(R* v, R head, int lane) {
+    R carry = head;                // value entering lane 0 of the current super-row
+#pragma unroll
+    for (int s = 0; s < SROWS; ++s) {
+        const R rot = __shfl_sync(0xffffffffu, v[s * LB + LB - 1], (lane + 31) & 31);
+        const R in0 = (lane == 0) ? carry : rot;
+        carry = rot;               // lane 0 sees lane 31's last element: head of the next super-row
+#pragma unroll
+        for (int j = LB - 1; j >= 1; --j) v[s * LB + j] = v[s * LB + j - 1];
+        v[s * LB] = in0;
+    }
+}
+
+template <typename R, int S>
+struct LevState {
+    R x[S * LB], y[S * LB], yh[S * LB], rh[S * LB];
+    R alpha, beta;
+};
+
+// all steps k in super-row SC (k = SC*128 .. SC*128+127), then recurse to SC+1
+template <typename R, int S, int SC, bool DURBIN>
+__device__ __forceinline__ void run_superrows(LevState<R, S>& st, int n, int lane, const R* r_s, const R* b_s) {
+    if constexpr (SC < S) {
+        constexpr int ACT = (SC + 1) * LB;
+        for (int lb = 0; lb < 32; ++lb) {
+#pragma unroll
+            for (int j = 0; j < LB; ++j) {
+                const int k = SC * LSPAN + lb * LB + j;
+                if (k == 0 || k >= n) continue;
+                st.beta *= ((R)1 - st.alpha * st.alpha);
+                R d1 = 0, d2 = 0;
+#pragma unroll
+                for (int i = 0; i < ACT; ++i) {
+                    if (!DURBIN) d1 = fma(st.rh[i], st.x[i], d1);
+                    d2 = fma(st.rh[i], st.y[i], d2);
+                }
+                if (!DURBIN) d1 = warp_sum(d1);
+                d2 = warp_sum(d2);
+                if (!DURBIN) {
+                    const R mu = (b_s[k] - d1) / st.beta;
+#pragma unroll
+                    for (int i = 0; i < ACT; ++i) st.x[i] = fma(mu, st.yh[i], st.x[i]);
+                    if (lane == lb) st.x[SC * LB + j] = mu;
+                }
+                if (DURBIN || k < n - 1) {
+                    const R rk = r_s[k];
+                    st.alpha = -(rk + d2) / st.beta;
+#pragma unroll
+                    for (int i = 0; i < ACT; ++i) {
+                        const R yo = st.y[i];
+                        st.y[i] = fma(st.alpha, st.yh[i], yo);
+                        st.yh[i] = fma(st.alpha, yo, st.yh[i]);
+                    }
+                    if (lane == lb) st.y[SC * LB + j] = st.alpha;
+                    shift_up<R, SC + 1>(st.yh, st.alpha, lane);
+                    shift_up<R, SC + 1>(st.rh, rk, lane);
+                }
+            }
+        }
+        run_superrows<R, S, SC + 1, DURBIN>(st, n, lane, r_s, b_s);
+    }
+}
+
+template <typename R, int S, bool DURBIN>
+__global__ void __launch_bounds__(128)
+k_levinson_warp(int64_t n64, int64_t nsys, const R* __restrict__ Rm, int64_t ldr, const R* __restrict__ Bm,
+                int64_t ldb, R* __restrict__ Xm, int64_t ldx, const R* __restrict__ diag) {
+    constexpr int NREG = S * LB;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int n = (int)n64;
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const int64_t sys = (int64_t)blockIdx.x * (blockDim.x >> 5) + wic;
+    if (sys >= nsys) return;
+    const int nr = DURBIN ? n : n - 1;                     // entries of r
+    R* r_s = reinterpret_cast<R*>(smraw) + (size_t)wic * (2 * S * LSPAN);
+    R* b_s = r_s + S * LSPAN;
+    const R dg = (!DURBIN && diag) ? diag[sys] : (R)1;
+    const bool scale = (dg != (R)1);
+    for (int i = lane; i < nr; i += 32) {
+        const R v = Rm[sys * ldr + i];
+        r_s[i] = scale ? v / dg : v;
+    }
+    if (!DURBIN)
+        for (int i = lane; i < n; i += 32) b_s[i] = Bm[sys * ldb + i];
+    __syncwarp();
+
+    LevState<R, S> st;
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) { st.x[i] = 0; st.y[i] = 0; st.yh[i] = 0; st.rh[i] = 0; }
+    if (n == 1 && !DURBIN) {          // 1x1 system: x = b (levinson! with empty r is not reachable in the reference)
+        if (lane == 0) Xm[sys * ldx] = scale ? b_s[0] / dg : b_s[0];
+        return;
+    }
+    const R r0 = r_s[0];
+    if (lane == 0) { st.y[0] = -r0; st.yh[0] = -r0; st.rh[0] = r0; if (!DURBIN) st.x[0] = b_s[0]; }
+    st.alpha = -r0;
+    st.beta = (R)1;
+    run_superrows<R, S, 0, DURBIN>(st, n, lane, r_s, b_s);
+
+    R* out = Xm + sys * ldx;
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int j = 0; j < LB; ++j) {
+            const int i = s * LSPAN + lane * LB + j;
+            if (i < n) {
+                R v = DURBIN ? st.y[s * LB + j] : st.x[s * LB + j];
+                if (scale) v /= dg;
+                out[i] = v;
+            }
+        }
+}
+
+// Fallback for n > 512: one CTA per system, iterates in shared memory (double-buffered y).
+template <typename R, bool DURBIN>
+__global__ void __launch_bounds__(256)
+k_levinson_block(int64_t n64, int64_t nsys, const R* __restrict__ Rm, int64_t ldr, const R* __restrict__ Bm,
+                 int64_t ldb, R* __restrict__ Xm, int64_t ldx, const R* __restrict__ diag) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int n = (int)n64;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    R* r_s = reinterpret_cast<R*>(smraw);
+    R* b_s = r_s + n;
+    R* x_s = b_s + n;
+    R* y0 = x_s + n;
+    R* y1 = y0 + n;
+    __shared__ R red[2][8];
+    __shared__ R sc[2];
+    for (int64_t sys = blockIdx.x; sys < nsys; sys += gridDim.x) {
+        const int nr = DURBIN ? n : n - 1;
+        const R dg = (!DURBIN && diag) ? diag[sys] : (R)1;
+        const bool scale = (dg != (R)1);
+        for (int i = tid; i < n; i += nth) {
+            r_s[i] = (i < nr) ? (scale ? Rm[sys * ldr + i] / dg : Rm[sys * ldr + i]) : (R)0;
+            b_s[i] = DURBIN ? (R)0 : Bm[sys * ldb + i];
+            x_s[i] = 0; y0[i] = 0; y1[i] = 0;
+        }
+        __syncthreads();
+        if (tid == 0) { y0[0] = -r_s[0]; x_s[0] = b_s[0]; }
+        R alpha = -r_s[0], beta = 1;
+        R* yc = y0; R* yn = y1;
+        __syncthreads();
+        for (int k = 1; k < n; ++k) {
+            beta *= ((R)1 - alpha * alpha);
+            R d1 = 0, d2 = 0;
+            for (int i = tid; i < k; i += nth) {
+                const R rr = r_s[k - 1 - i];
+                if (!DURBIN) d1 = fma(rr, x_s[i], d1);
+                d2 = fma(rr, yc[i], d2);
+            }
+            d1 = warp_sum(d1); d2 = warp_sum(d2);
+            if ((tid & 31) == 0) { red[0][tid >> 5] = d1; red[1][tid >> 5] = d2; }
+            __syncthreads();
+            if (tid == 0) {
+                R s1 = 0, s2 = 0;
+                for (int w = 0; w < (nth >> 5); ++w) { s1 += red[0][w]; s2 += red[1][w]; }
+                sc[0] = s1; sc[1] = s2;
+            }
+            __syncthreads();
+            d1 = sc[0]; d2 = sc[1];
+            if (!DURBIN) {
+                const R mu = (b_s[k] - d1) / beta;
+                for (int i = tid; i < k; i += nth) x_s[i] = fma(mu, yc[k - 1 - i], x_s[i]);
+                if (tid == 0) x_s[k] = mu;
+            }
+            if (DURBIN || k < n - 1) {
+                alpha = -(r_s[k] + d2) / beta;
+                for (int i = tid; i < k; i += nth) yn[i] = fma(alpha, yc[k - 1 - i], yc[i]);
+                if (tid == 0) yn[k] = alpha;
+                R* t = yc; yc = yn; yn = t;
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < n; i += nth) {
+            R v = DURBIN ? yc[i] : x_s[i];
+            if (scale) v /= dg;
+            Xm[sys * ldx + i] = v;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename R, bool DURBIN>
+static int launch_levinson(int64_t n, int64_t nsys, const R* r, int64_t ldr, const R* b, int64_t ldb, R* x,
+                           int64_t ldx, const R* diag, cudaStream_t s) {
+    if (nsys <= 0 || n <= 0) return TB200_OK;
+    if (n <= 4 * LSPAN) {
+        const int S = (int)((n + LSPAN - 1) / LSPAN);
+        const int wpc = 4;
+        const unsigned grid = (unsigned)((nsys + wpc - 1) / wpc);
+        const size_t smem = (size_t)wpc * 2 * S * LSPAN * sizeof(R);
+#define TB_LEV_CASE(SV)                                                                          \
+    case SV:                                                                                     \
+        k_levinson_warp<R, SV, DURBIN><<<grid, wpc * 32, smem, s>>>(n, nsys, r, ldr, b, ldb, x, ldx, diag); \
+        break;
+        switch (S) {
+            TB_LEV_CASE(1) TB_LEV_CASE(2) TB_LEV_CASE(3) TB_LEV_CASE(4)
+        }
+#undef TB_LEV_CASE
+        count_launch();
+        return cuda_status(cudaGetLastError(), "levinson warp kernel");
+    }
+    const size_t smem = (size_t)5 * n * sizeof(R);
+    if (smem > 200 * 1024) return set_error(TB200_UNSUPPORTED, "levinson/durbin: n too large for the shared-memory kernel");
+    auto kern = k_levinson_block<R, DURBIN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "levinson smem attribute");
+    const unsigned grid = (unsigned)(nsys < 148 * 8 ? nsys : 148 * 8);
+    kern<<<grid, 256, smem, s>>>(n, nsys, r, ldr, b, ldb, x, ldx, diag);
+    count_launch();
+    return cuda_status(cudaGetLastError(), "levinson block kernel");
+}
+
+int levinson_dispatch(int dtype, bool durbin, int64_t n, int64_t nsys, const void* r, int64_t ldr, const void* b,
+                      int64_t ldb, void* x, int64_t ldx, const void* diag, cudaStream_t s) {
+    if (dtype == TB200_F64) {
+        return durbin ? launch_levinson<double, true>(n, nsys, (const double*)r, ldr, nullptr, 0, (double*)x, ldx, nullptr, s)
+                      : launch_levinson<double, false>(n, nsys, (const double*)r, ldr, (const double*)b, ldb, (double*)x, ldx, (const double*)diag, s);
+    }
+    if (dtype == TB200_F32) {
+        return durbin ? launch_levinson<float, true>(n, nsys, (const float*)r, ldr, nullptr, 0, (float*)x, ldx, nullptr, s)
+                      : launch_levinson<float, false>(n, nsys, (const float*)r, ldr, (const float*)b, ldb, (float*)x, ldx, (const float*)diag, s);
+    }
+    return set_error(TB200_UNSUPPORTED, "levinson/durbin: only real Float32/Float64 systems");
+}
+
+}  // namespace tb
