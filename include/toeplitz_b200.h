@@ -148,6 +148,10 @@ int tb200_spectrum_buffer(tb200_handle_t h, void** ptr, int64_t* bytes);
 /* tuning / introspection: number of kernel launches issued by this library so far      */
 int64_t tb200_launch_count(void);
 int tb200_set_option(const char* name, int64_t value);
+/* with option "time_passes" = 1 every FFT pass is bracketed by CUDA events on its stream;
+ * this drains them: summed milliseconds and launch counts for {cols A, rows B, cols C,
+ * single-kernel rows}.  Synchronises on the recorded events.                            */
+int tb200_pass_times(double ms[4], int64_t counts[4]);
 
 #ifdef __cplusplus
 }

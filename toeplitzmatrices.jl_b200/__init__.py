@@ -11,4 +11,4 @@ from .api import (Toeplitz, SymmetricToeplitz, Circulant, LowerTriangularToeplit
                   Hankel, ToeplitzFactorization, factorize, mul_, mul, ldiv_, ldiv, circ_ldiv_, eigvals, det, inv,
                   pinv, sqrt, circ_mul, adjoint, transpose, strang, chan, durbin, durbin_, levinson, levinson_,
                   cgs, cg, colmajor, to_colmajor, mul_host_, factorize_host, spectrum_tensor,
-                  factorize_empty_like, launch_count, set_option)
+                  factorize_empty_like, launch_count, set_option, pass_times)

@@ -756,3 +756,12 @@ def launch_count() -> int:
 
 def set_option(name: str, value: int) -> None:
     check(L.lib().tb200_set_option(name.encode(), int(value)))
+
+
+def pass_times():
+    """Drain the per-pass CUDA-event timers: ({name: ms}, {name: launches})."""
+    ms = (ctypes.c_double * 4)()
+    cnt = (ctypes.c_int64 * 4)()
+    check(L.lib().tb200_pass_times(ms, cnt))
+    names = ("cols_A", "rows_B", "cols_C", "rows_single")
+    return {k: ms[i] for i, k in enumerate(names)}, {k: cnt[i] for i, k in enumerate(names)}

@@ -27,6 +27,27 @@ static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static std::atomic<long long> g_group_bytes{48ll << 20};   // two-level scratch budget per group
 static std::atomic<long long> g_host_chunk_bytes{256ll << 20};
+static std::atomic<int> g_time_passes{0};
+
+// optional per-pass device timing (bench.py's roofline leg): CUDA events recorded on the
+// launching stream around every pass while "time_passes" is on.
+struct PassEvents { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; };
+static std::mutex g_pass_mutex;
+static PassEvents g_pass[4];      // 0 = cols A, 1 = rows B, 2 = cols C, 3 = single-kernel rows
+
+struct PassTimer {
+    int which; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr; bool on;
+    PassTimer(int w, cudaStream_t st) : which(w), s(st), on(g_time_passes.load() != 0) {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+    }
+    ~PassTimer() {
+        if (on) {
+            cudaEventRecord(b, s);
+            std::lock_guard<std::mutex> lock(g_pass_mutex);
+            g_pass[which].ev.emplace_back(a, b);
+        }
+    }
+};
 
 int set_error(int status, const char* fmt, ...) {
     va_list ap;
@@ -113,23 +134,43 @@ static void fill_twiddles(std::vector<cx<R>>& v, long long count, long long stri
 }
 
 struct TwTables {
-    std::shared_ptr<DevBuf> f32, f64;
+    std::shared_ptr<DevBuf> f32[MAX_LOG2L + 1], f64[MAX_LOG2L + 1];
 };
 static std::mutex g_tw_mutex;
 static TwTables g_tw[64];
 
+// stage twiddle table (thread order, see fft_core.cuh) for an L = 2^log2l transform
 template <typename R>
-static int global_twiddles(const cx<R>** out) {
+static int stage_twiddles(int log2l, const cx<R>** out) {
     int dev = 0;
     TB_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
+    if (log2l < LOGE || log2l > MAX_LOG2L) return set_error(TB200_UNSUPPORTED, "no stage table for 2^%d", log2l);
     std::lock_guard<std::mutex> lock(g_tw_mutex);
-    std::shared_ptr<DevBuf>& slot = (sizeof(R) == 8) ? g_tw[dev].f64 : g_tw[dev].f32;
+    std::shared_ptr<DevBuf>& slot = (sizeof(R) == 8) ? g_tw[dev].f64[log2l] : g_tw[dev].f32[log2l];
     if (!slot) {
-        std::vector<cx<R>> h;
-        fill_twiddles<R>(h, TWN, 1, TWN);
+        std::vector<cx<R>> h((size_t)std::max(stage_tw_total(log2l), 1));
+        const long double twopi = 6.283185307179586476925286766559005768L;
+        for (int k = 0; k < log2l / LOGE; ++k) {
+            const int ls = log2l - LOGE * (k + 1);
+            if (ls <= 0) continue;
+            const long long s = 1ll << ls, period = s * E;
+            const int off = stage_tw_off(log2l, k);
+            for (int c = 1; c < E; ++c)
+                for (long long r = 0; r < s; ++r) {
+                    const long long num = (r * c) % period;
+                    long double cs = cosl(twopi * (long double)num / (long double)period);
+                    long double sn = sinl(twopi * (long double)num / (long double)period);
+                    if (num * 4 % period == 0) {
+                        const long long q = num * 4 / period;
+                        cs = (q == 0) ? 1 : (q == 2) ? -1 : 0;
+                        sn = (q == 1) ? 1 : (q == 3) ? -1 : 0;
+                    }
+                    h[(size_t)off + (size_t)(c - 1) * s + r] = mk<R>((R)cs, (R)(-sn));
+                }
+        }
         std::shared_ptr<DevBuf> b;
-        TB_TRY(dev_alloc(b, sizeof(cx<R>) * TWN, "twiddle table"));
-        TB_CUDA(cudaMemcpy(b->p, h.data(), sizeof(cx<R>) * TWN, cudaMemcpyHostToDevice), "twiddle upload");
+        TB_TRY(dev_alloc(b, sizeof(cx<R>) * h.size(), "twiddle table"));
+        TB_CUDA(cudaMemcpy(b->p, h.data(), sizeof(cx<R>) * h.size(), cudaMemcpyHostToDevice), "twiddle upload");
         slot = b;
     }
     *out = reinterpret_cast<const cx<R>*>(slot->p);
@@ -222,9 +263,11 @@ template <typename R>
 static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     ConvArgs<R> a;
     memset(&a, 0, sizeof(a));
-    const cx<R>* tw = nullptr;
-    TB_TRY(global_twiddles<R>(&tw));
-    a.tw = tw;
+    const cx<R>* tw_rows = nullptr;
+    const cx<R>* tw_cols = nullptr;
+    TB_TRY(stage_twiddles<R>(h->log2l2, &tw_rows));
+    if (h->two_level) TB_TRY(stage_twiddles<R>(h->log2l1, &tw_cols));
+    a.tw = tw_rows;
     a.x = c.x; a.ldx = c.ldx; a.x_mode = c.x_mode; a.n_in = c.n_in; a.reverse_x = c.reverse_x;
     a.y = c.y; a.ldy = c.ldy; a.y_mode = c.y_mode; a.m_out = c.m_out;
     a.ncols = c.ncols; a.nfft = c.nfft;
@@ -235,6 +278,7 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     if (c.nfft <= 0) return TB200_OK;
     if (!h->two_level) {
         count_launch();
+        PassTimer pt(3, s);
         return cuda_status(launch_rows<R>(h->log2l2, a, num_sms(), s), "k_rows");
     }
     // ---- two-level: A (strided cols, fwd) -> B (rows: fwd * spec inv) -> C (strided cols, inv)
@@ -256,10 +300,12 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
         if (c.do_fwd) {
             ConvArgs<R> pa = a;
             pa.nfft = g;
+            pa.tw = tw_cols;
             pa.ncols = c.ncols - f0 * cols_per_fft;
             if (c.x_mode == IO_SPEC) return set_error(TB200_BAD_ARG, "internal: IO_SPEC input with forward transform");
             pa.x = reinterpret_cast<const char*>(c.x) + (size_t)f0 * cols_per_fft * c.ldx * in_esz;
             count_launch();
+            PassTimer pt(0, s);
             TB_CUDA(launch_colsA<R>(h->log2l1, h->ta, pa, s), "k_colsA");
         }
         // pass B: rows of the scratch, in place
@@ -280,15 +326,18 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
                 if (g != 1 || c.nfft != 1) return set_error(TB200_BAD_ARG, "internal: forward-only runs one transform");
             }
             count_launch();
+            PassTimer pt(1, s);
             TB_CUDA(launch_rows<R>(h->log2l2, pb, num_sms(), s), "k_rows (pass B)");
         }
         // pass C
         if (c.do_inv) {
             ConvArgs<R> pc = a;
             pc.nfft = g;
+            pc.tw = tw_cols;
             pc.ncols = c.ncols - f0 * cols_per_fft;
             pc.y = reinterpret_cast<char*>(c.y) + (size_t)f0 * cols_per_fft * c.ldy * out_esz;
             count_launch();
+            PassTimer pt(2, s);
             TB_CUDA(launch_colsC<R>(h->log2l1, h->ta, pc, s), "k_colsC");
         }
     }
@@ -366,10 +415,27 @@ const char* tb200_version(void) { return "toeplitz_b200 0.1.0 (sm_100a)"; }
 const char* tb200_last_error(void) { return g_err; }
 int64_t tb200_launch_count(void) { return g_launches.load(); }
 
+int tb200_pass_times(double ms[4], int64_t counts[4]) {
+    if (!ms || !counts) return set_error(TB200_BAD_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lock(g_pass_mutex);
+    for (int w = 0; w < 4; ++w) {
+        ms[w] = 0; counts[w] = 0;
+        for (auto& pr : g_pass[w].ev) {
+            float t = 0;
+            cudaEventSynchronize(pr.second);
+            if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) { ms[w] += t; counts[w] += 1; }
+            cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+        }
+        g_pass[w].ev.clear();
+    }
+    return TB200_OK;
+}
+
 int tb200_set_option(const char* name, int64_t value) {
     if (!name) return set_error(TB200_BAD_ARG, "option name is NULL");
     if (!strcmp(name, "group_bytes")) { g_group_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "host_chunk_bytes")) { g_host_chunk_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
+    if (!strcmp(name, "time_passes")) { g_time_passes = value ? 1 : 0; return TB200_OK; }
     return set_error(TB200_BAD_ARG, "unknown option '%s'", name);
 }
 
@@ -489,8 +555,14 @@ int tb200_mul_host(tb200_handle_t h, void* y_host, int64_t ldy, int ydtype, cons
     int64_t cc = std::max<int64_t>(2, g_host_chunk_bytes.load() / (int64_t)std::max<size_t>(h->n * xsz, h->m * ysz));
     cc &= ~int64_t(1);
     cc = std::min<int64_t>(cc, (ncols + 1) & ~int64_t(1));
-    const int NS = 2;
+    const int NS = 3;
     std::shared_ptr<DevBuf> xd[NS], yd[NS];
+    // one contiguous copy when the host matrix is packed, else a pitched copy
+    auto copy2d = [](void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows,
+                     cudaMemcpyKind kind, cudaStream_t st) {
+        if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * rows, kind, st);
+        return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st);
+    };
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[NS], ev_cmp[NS], ev_out[NS];
     int st = TB200_OK;
@@ -528,11 +600,11 @@ int tb200_mul_host(tb200_handle_t h, void* y_host, int64_t ldy, int ydtype, cons
             TB_HOSTTRY(cuda_status(cudaStreamWaitEvent(s_in, ev_cmp[sl], 0), "wait"));
             TB_HOSTTRY(cuda_status(cudaStreamWaitEvent(s_in, ev_out[sl], 0), "wait"));
         }
-        TB_HOSTTRY(cuda_status(cudaMemcpy2DAsync(xd[sl]->p, (size_t)h->n * xsz, xs, (size_t)ldx * xsz, (size_t)h->n * xsz,
-                                                 (size_t)nc, cudaMemcpyHostToDevice, s_in), "x upload"));
+        TB_HOSTTRY(cuda_status(copy2d(xd[sl]->p, (size_t)h->n * xsz, xs, (size_t)ldx * xsz, (size_t)h->n * xsz,
+                                      (size_t)nc, cudaMemcpyHostToDevice, s_in), "x upload"));
         if (has_beta)
-            TB_HOSTTRY(cuda_status(cudaMemcpy2DAsync(yd[sl]->p, (size_t)h->m * ysz, ys, (size_t)ldy * ysz, (size_t)h->m * ysz,
-                                                     (size_t)nc, cudaMemcpyHostToDevice, s_in), "y upload"));
+            TB_HOSTTRY(cuda_status(copy2d(yd[sl]->p, (size_t)h->m * ysz, ys, (size_t)ldy * ysz, (size_t)h->m * ysz,
+                                          (size_t)nc, cudaMemcpyHostToDevice, s_in), "y upload"));
         TB_HOSTTRY(cuda_status(cudaEventRecord(ev_in[sl], s_in), "record"));
         // compute
         TB_HOSTTRY(cuda_status(cudaStreamWaitEvent(s_cmp, ev_in[sl], 0), "wait"));
@@ -540,8 +612,8 @@ int tb200_mul_host(tb200_handle_t h, void* y_host, int64_t ldy, int ydtype, cons
         TB_HOSTTRY(cuda_status(cudaEventRecord(ev_cmp[sl], s_cmp), "record"));
         // D2H
         TB_HOSTTRY(cuda_status(cudaStreamWaitEvent(s_out, ev_cmp[sl], 0), "wait"));
-        TB_HOSTTRY(cuda_status(cudaMemcpy2DAsync(ys, (size_t)ldy * ysz, yd[sl]->p, (size_t)h->m * ysz, (size_t)h->m * ysz,
-                                                 (size_t)nc, cudaMemcpyDeviceToHost, s_out), "y download"));
+        TB_HOSTTRY(cuda_status(copy2d(ys, (size_t)ldy * ysz, yd[sl]->p, (size_t)h->m * ysz, (size_t)h->m * ysz,
+                                      (size_t)nc, cudaMemcpyDeviceToHost, s_out), "y download"));
         TB_HOSTTRY(cuda_status(cudaEventRecord(ev_out[sl], s_out), "record"));
     }
     TB_HOSTTRY(cuda_status(cudaStreamSynchronize(s_out), "host-path sync"));

@@ -21,8 +21,7 @@ namespace tb {
 
 constexpr int LOGE = 4;          // 16 points per thread
 constexpr int E = 1 << LOGE;
-constexpr int LOG2TWN = 14;      // twiddle table length (max single-pass FFT: 16384)
-constexpr int TWN = 1 << LOG2TWN;
+constexpr int MAX_LOG2L = 14;    // longest single-pass FFT (16384 points, Float32 only)
 
 template <typename R> struct CxT;
 template <> struct CxT<float> { using type = float2; };
@@ -53,6 +52,20 @@ __host__ __device__ constexpr int brev(int x, int bits) {
     return r;
 }
 __host__ __device__ constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
+
+// Per-length stage twiddle table: stage k (stride s = L/16^(k+1) > 1) owns the block
+//   T[off_k + (c-1)*s + r] = exp(-2 pi i r c / (16 s)),  c = 1..15, r = 0..s-1
+// so a warp reads consecutive entries (thread order) and late stages touch only a few
+// hundred bytes that stay in L1.
+__host__ __device__ constexpr int stage_tw_off(int log2l, int k) {
+    int off = 0;
+    for (int kk = 0; kk < k; ++kk) {
+        int ls = log2l - LOGE * (kk + 1);
+        if (ls > 0) off += (E - 1) << ls;
+    }
+    return off;
+}
+__host__ __device__ constexpr int stage_tw_total(int log2l) { return stage_tw_off(log2l, log2l / LOGE); }
 
 // d * exp(-/+ 2 pi i k/16); k is a compile-time constant after unrolling.
 template <typename R, bool INV>
@@ -165,7 +178,7 @@ struct SlotFFT {
             if (ls > 0) {
 #pragma unroll
                 for (int c = 1; c < E; ++c) {
-                    cx<R> w = ldg_cx<R>(tw + ((r * c) << (LOG2TWN - LOGE - ls)));
+                    cx<R> w = ldg_cx<R>(tw + (stage_tw_off(LOG2L, k) + (c - 1) * s + r));
                     a[brev(c, LOGE)] = cmul(a[brev(c, LOGE)], w);
                 }
             }
@@ -217,7 +230,7 @@ struct SlotFFT {
             if (ls > 0) {
 #pragma unroll
                 for (int c = 1; c < E; ++c) {
-                    cx<R> w = ldg_cx<R>(tw + ((r * c) << (LOG2TWN - LOGE - ls)));
+                    cx<R> w = ldg_cx<R>(tw + (stage_tw_off(LOG2L, k) + (c - 1) * s + r));
                     a[brev(c, LOGE)] = cmulc(a[brev(c, LOGE)], w);
                 }
             }

@@ -82,8 +82,17 @@ __device__ __forceinline__ void store_elem(const ConvArgs<R>& p, long long f, lo
 }
 
 // ---- contiguous transforms -------------------------------------------------------------
+// occupancy target: 128 registers/thread for Float64, 64 for Float32, limited by shared memory
+template <typename R>
+constexpr int min_ctas(int threads, int smem_bytes) {
+    int by_regs = 65536 / (threads * (sizeof(R) == 8 ? 128 : 64));
+    int by_smem = (220 * 1024) / (smem_bytes > 0 ? smem_bytes : 1);
+    int m = by_regs < by_smem ? by_regs : by_smem;
+    return m < 1 ? 1 : m;
+}
+
 template <typename R, int LOG2L, int TS>
-__global__ void __launch_bounds__((1 << LOG2L) / E * TS)
+__global__ void __launch_bounds__((1 << LOG2L) / E * TS, min_ctas<R>((1 << LOG2L) / E * TS, (int)sizeof(cx<R>) * (1 << LOG2L) * TS))
 k_rows(const ConvArgs<R> p) {
     using F = SlotFFT<R, LOG2L>;
     constexpr int L = F::L, NT = F::NT;
@@ -136,7 +145,7 @@ __device__ __forceinline__ cx<R> level_twiddle(const ConvArgs<R>& p, long long m
 
 // grid.x = (N2/TA) * nfft ; block = TA * NT1
 template <typename R, int LOG2L1, int TA>
-__global__ void __launch_bounds__((1 << LOG2L1) / E * TA)
+__global__ void __launch_bounds__((1 << LOG2L1) / E * TA, min_ctas<R>((1 << LOG2L1) / E * TA, (int)sizeof(cx<R>) * (1 << LOG2L1) * TA))
 k_colsA(const ConvArgs<R> p) {
     using F = SlotFFT<R, LOG2L1>;
     constexpr int NT = F::NT;
@@ -165,7 +174,7 @@ k_colsA(const ConvArgs<R> p) {
 }
 
 template <typename R, int LOG2L1, int TA>
-__global__ void __launch_bounds__((1 << LOG2L1) / E * TA)
+__global__ void __launch_bounds__((1 << LOG2L1) / E * TA, min_ctas<R>((1 << LOG2L1) / E * TA, (int)sizeof(cx<R>) * (1 << LOG2L1) * TA))
 k_colsC(const ConvArgs<R> p) {
     using F = SlotFFT<R, LOG2L1>;
     constexpr int NT = F::NT;
