@@ -190,6 +190,13 @@ def run_ours(args):
     n = 1 << LOG2N
     ncols = args.cols
     vc, vr = coefficient_vectors()
+    if args.group_mb:
+        tb.set_option("group_bytes", args.group_mb << 20)
+    if args.no_overlap:
+        tb.set_option("overlap_streams", 0)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        tb.set_option(k, int(v))
 
     # factorize on rank 0, broadcast the spectrum once (the only exchange on the path)
     if rank == 0:
@@ -334,6 +341,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-pass-events", action="store_true", help="do not bracket each pass with CUDA events")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
+    ap.add_argument("--group-mb", type=int, default=0, help="tuning: two-level workspace budget per group (MiB)")
+    ap.add_argument("--no-overlap", action="store_true", help="tuning: disable the two-stream group overlap")
+    ap.add_argument("--opt", action="append", default=[], help="tuning: library option name=value (repeatable)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

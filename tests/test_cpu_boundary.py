@@ -62,9 +62,13 @@ def test_missing_library_fails_loudly(monkeypatch):
         _lib.lib()
 
 
+@pytest.mark.parametrize("loge", [3, 4])
 @pytest.mark.parametrize("l", [4, 5, 6, 7, 8, 9])
-def test_fft_index_model_single_level(l):
-    from fft_model import Slot, E, unscramble
+def test_fft_index_model_single_level(l, loge):
+    import fft_model
+    from fft_model import Slot, unscramble
+    fft_model.set_radix(loge)
+    E = fft_model.E
     rng = np.random.default_rng(l)
     S = Slot(l)
     x = rng.standard_normal(S.L) + 1j * rng.standard_normal(S.L)
@@ -79,9 +83,12 @@ def test_fft_index_model_single_level(l):
         assert S.freq_of_pos(S.pos_of_freq(k)) == k
 
 
+@pytest.mark.parametrize("loge", [3, 4])
 @pytest.mark.parametrize("l1,l2", [(4, 4), (6, 5), (5, 7)])
-def test_fft_index_model_two_level(l1, l2):
+def test_fft_index_model_two_level(l1, l2, loge):
+    import fft_model
     from fft_model import two_level_forward, unscramble
+    fft_model.set_radix(loge)
     rng = np.random.default_rng(l1 * 10 + l2)
     Np = 1 << (l1 + l2)
     x = rng.standard_normal(Np) + 1j * rng.standard_normal(Np)

@@ -3,7 +3,12 @@
 tests to prove the index maps of the CUDA kernels without a GPU."""
 import numpy as np
 
-LOGE, E = 4, 16
+LOGE, E = 4, 16          # default points per thread; set_radix() switches the model
+
+
+def set_radix(loge):
+    global LOGE, E
+    LOGE, E = loge, 1 << loge
 
 
 def brev(x, bits):

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtoeplitz_b200.so")
+LIB_PATH = os.environ.get("TB200_LIB") or os.path.join(_HERE, "lib", "libtoeplitz_b200.so")   # TB200_LIB: experiment builds
 
 OK, DIM_MISMATCH, BAD_ARG, UNSUPPORTED, CUDA_ERR, OOM = range(6)
 F32, F64, C32, C64 = range(4)

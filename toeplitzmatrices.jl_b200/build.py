@@ -53,6 +53,30 @@ def _compile(src: str, force: bool, hdr_t: float) -> str:
     return obj
 
 
+def build_variant(tag: str, defines) -> str:
+    """Experiment build: objects and library suffixed with `tag`, extra -D flags (never the default)."""
+    objdir = os.path.join(HERE, "build", tag)
+    os.makedirs(objdir, exist_ok=True)
+    os.makedirs(LIBDIR, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + ["-D" + d for d in defines]
+
+    def one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        r = subprocess.run([_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(r.stderr)
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(one, SOURCES))
+    lib = os.path.join(LIBDIR, "libtoeplitz_b200_%s.so" % tag)
+    r = subprocess.run([_nvcc(), "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+                        "-Xcompiler", "-fPIC", "-cudart", "static"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr)
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
@@ -72,4 +96,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        build(force="--force" in sys.argv, verbose=True)

@@ -120,15 +120,15 @@ __global__ void k_spec_mul(cx<R>* __restrict__ out, const cx<R>* __restrict__ a,
 // src/linearalgebra.jl:286-287).  two_level: k = k1 + N1*k2, row p = pos1(k1).
 template <typename R>
 __global__ void k_unscramble(cx<R>* __restrict__ out, const cx<R>* __restrict__ spec, long long Np,
-                             int log2l1, int log2l2) {
-    PlanDims d2{log2l2};
+                             int log2l1, int log2l2, int le) {
+    PlanDims d2{log2l2, le};
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < Np;
          k += (long long)gridDim.x * blockDim.x) {
         long long off;
         if (log2l1 == 0) {
             off = d2.layout_of_pos(d2.pos_of_freq((int)k));
         } else {
-            PlanDims d1{log2l1};
+            PlanDims d1{log2l1, le};
             const int k1 = (int)(k & ((1LL << log2l1) - 1));
             const int k2 = (int)(k >> log2l1);
             const long long p = d1.pos_of_freq(k1);

@@ -28,6 +28,8 @@ static std::atomic<long long> g_launches{0};
 static std::atomic<long long> g_group_bytes{48ll << 20};   // two-level scratch budget per group
 static std::atomic<long long> g_host_chunk_bytes{256ll << 20};
 static std::atomic<int> g_time_passes{0};
+static std::atomic<int> g_overlap_streams{1};
+static std::atomic<int> g_l2max_f64{12}, g_l2max_f32{13}, g_ta_cap{0};   // plan tuning knobs
 
 // optional per-pass device timing (bench.py's roofline leg): CUDA events recorded on the
 // launching stream around every pass while "time_passes" is on.
@@ -144,17 +146,18 @@ template <typename R>
 static int stage_twiddles(int log2l, const cx<R>** out) {
     int dev = 0;
     TB_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
+    constexpr int LOGE = le_of<R>(), E = 1 << LOGE;
     if (log2l < LOGE || log2l > MAX_LOG2L) return set_error(TB200_UNSUPPORTED, "no stage table for 2^%d", log2l);
     std::lock_guard<std::mutex> lock(g_tw_mutex);
     std::shared_ptr<DevBuf>& slot = (sizeof(R) == 8) ? g_tw[dev].f64[log2l] : g_tw[dev].f32[log2l];
     if (!slot) {
-        std::vector<cx<R>> h((size_t)std::max(stage_tw_total(log2l), 1));
+        std::vector<cx<R>> h((size_t)std::max(stage_tw_total(log2l, LOGE), 1));
         const long double twopi = 6.283185307179586476925286766559005768L;
         for (int k = 0; k < log2l / LOGE; ++k) {
             const int ls = log2l - LOGE * (k + 1);
             if (ls <= 0) continue;
             const long long s = 1ll << ls, period = s * E;
-            const int off = stage_tw_off(log2l, k);
+            const int off = stage_tw_off(log2l, k, LOGE);
             for (int c = 1; c < E; ++c)
                 for (long long r = 0; r < s; ++r) {
                     const long long num = (r * c) % period;
@@ -189,9 +192,20 @@ struct tb200_fact {
     int64_t m = 0, n = 0, Np = 0;
     int log2np = 0, two_level = 0, log2l1 = 0, log2l2 = 0, ta = 0;
     int reverse_x = 0;
-    std::shared_ptr<DevBuf> spec, inv_spec, tw_lo, tw_hi, scratch;
+    std::shared_ptr<DevBuf> spec, inv_spec, tw_lo, tw_hi, scratch, scratch2;
     int tw_hb = 0;
     bool spec_valid = false;
+    // two helper streams: consecutive column groups of a two-level product alternate between them so
+    // the tail of one pass overlaps the next group's passes (each stream owns one workspace)
+    cudaStream_t hs[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    ~tb200_fact() {
+        for (int i = 0; i < 2; ++i) {
+            if (hs[i]) cudaStreamDestroy(hs[i]);
+            if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+        }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+    }
 };
 
 namespace tb {
@@ -201,12 +215,12 @@ static int next_log2(int64_t v) { int l = 0; while ((1ll << l) < v) ++l; return 
 static int make_plan(tb200_fact* h) {
     const int l = h->log2np;
     const int max_single = h->prec ? 12 : 13;
-    if (l < LOGE) return set_error(TB200_UNSUPPORTED, "embedding shorter than 16 is handled by tb200_mul_direct");
+    if (l < 4) return set_error(TB200_UNSUPPORTED, "embedding shorter than 16 is handled by tb200_mul_direct");
     if (l <= max_single) {
         h->two_level = 0; h->log2l1 = 0; h->log2l2 = l; h->ta = 0;
         return TB200_OK;
     }
-    const int l2max = h->prec ? 12 : 13;
+    const int l2max = h->prec ? g_l2max_f64.load() : g_l2max_f32.load();
     int l1 = std::max(l - l2max, std::min(9, l / 2));
     int l2 = l - l1;
     const int l1max = h->prec ? 11 : 12;
@@ -219,6 +233,7 @@ static int make_plan(tb200_fact* h) {
     int ta = full;
     const size_t esz = h->prec ? 16 : 8;
     while (ta > 4 && ((size_t)1 << l1) * ta * esz > 128 * 1024) ta >>= 1;
+    if (g_ta_cap.load() >= 4 && ta > g_ta_cap.load()) ta = g_ta_cap.load();
     h->two_level = 1; h->log2l1 = l1; h->log2l2 = l2; h->ta = ta;
     // inter-level twiddles  w_Np^m = lo[m & mask] * hi[m >> hb]
     h->tw_hb = (l + 1) / 2;
@@ -286,16 +301,41 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     long long G = std::max(1ll, g_group_bytes.load() / (long long)(Np * sizeof(cx<R>)));
     G = std::min(G, c.nfft);
     TB_TRY(ensure_scratch(h, (size_t)G * Np * sizeof(cx<R>)));
-    cx<R>* scratch = reinterpret_cast<cx<R>*>(h->scratch->p);
-    a.scratch = scratch; a.log2n2 = h->log2l2;
+    const bool overlap = g_overlap_streams.load() && c.nfft > G && c.do_fwd && c.do_inv;
+    cx<R>* scratch_of[2] = {reinterpret_cast<cx<R>*>(h->scratch->p), reinterpret_cast<cx<R>*>(h->scratch->p)};
+    cudaStream_t stream_of[2] = {s, s};
+    if (overlap) {
+        if (!h->scratch2 || h->scratch2->bytes < (size_t)G * Np * sizeof(cx<R>)) {
+            h->scratch2.reset();
+            TB_TRY(dev_alloc(h->scratch2, (size_t)G * Np * sizeof(cx<R>), "second workspace"));
+        }
+        if (!h->hs[0]) {
+            for (int i = 0; i < 2; ++i) {
+                TB_CUDA(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking), "helper stream");
+                TB_CUDA(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming), "event");
+            }
+            TB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), "event");
+        }
+        scratch_of[1] = reinterpret_cast<cx<R>*>(h->scratch2->p);
+        stream_of[0] = h->hs[0]; stream_of[1] = h->hs[1];
+        TB_CUDA(cudaEventRecord(h->ev_fork, s), "fork");
+        TB_CUDA(cudaStreamWaitEvent(h->hs[0], h->ev_fork, 0), "fork");
+        TB_CUDA(cudaStreamWaitEvent(h->hs[1], h->ev_fork, 0), "fork");
+    }
+    cudaStream_t user_stream = s;
+    a.log2n2 = h->log2l2;
     a.tw_lo = reinterpret_cast<const cx<R>*>(h->tw_lo->p);
     a.tw_hi = reinterpret_cast<const cx<R>*>(h->tw_hi->p);
     a.tw_hb = h->tw_hb;
     const size_t in_esz = (c.x_mode == IO_REAL || c.x_mode == IO_PAIR) ? sizeof(R) : sizeof(cx<R>);
     const size_t out_esz = (c.y_mode == IO_REAL || c.y_mode == IO_PAIR) ? sizeof(R) : sizeof(cx<R>);
     const long long cols_per_fft = (c.x_mode == IO_PAIR || c.y_mode == IO_PAIR) ? 2 : 1;
-    for (long long f0 = 0; f0 < c.nfft; f0 += G) {
+    long long group_index = 0;
+    for (long long f0 = 0; f0 < c.nfft; f0 += G, ++group_index) {
         const long long g = std::min(G, c.nfft - f0);
+        cx<R>* scratch = scratch_of[group_index & 1];
+        s = stream_of[group_index & 1];
+        a.scratch = scratch;
         // pass A
         if (c.do_fwd) {
             ConvArgs<R> pa = a;
@@ -341,6 +381,12 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
             TB_CUDA(launch_colsC<R>(h->log2l1, h->ta, pc, s), "k_colsC");
         }
     }
+    if (overlap) {
+        for (int i = 0; i < 2; ++i) {
+            TB_CUDA(cudaEventRecord(h->ev_join[i], h->hs[i]), "join");
+            TB_CUDA(cudaStreamWaitEvent(user_stream, h->ev_join[i], 0), "join");
+        }
+    }
     return TB200_OK;
 }
 
@@ -377,7 +423,7 @@ static int new_handle(int kind, int dtype, int64_t m, int64_t n, tb200_fact** ou
     } else {
         h->Np = 1ll << next_log2(m + n - 1);
     }
-    if (h->Np < E) h->Np = E;
+    if (h->Np < 16) h->Np = 16;
     if (kind == TB200_CIRCULANT && h->Np != n)
         return set_error(TB200_UNSUPPORTED, "Circulant of size %lld < 16: use tb200_mul_direct / dense algebra", (long long)n);
     h->log2np = next_log2(h->Np);
@@ -436,6 +482,10 @@ int tb200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "group_bytes")) { g_group_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "host_chunk_bytes")) { g_host_chunk_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "time_passes")) { g_time_passes = value ? 1 : 0; return TB200_OK; }
+    if (!strcmp(name, "overlap_streams")) { g_overlap_streams = value ? 1 : 0; return TB200_OK; }
+    if (!strcmp(name, "l2max_f64")) { g_l2max_f64 = (int)value; return TB200_OK; }
+    if (!strcmp(name, "l2max_f32")) { g_l2max_f32 = (int)value; return TB200_OK; }
+    if (!strcmp(name, "ta_cap")) { g_ta_cap = (int)value; return TB200_OK; }
     return set_error(TB200_BAD_ARG, "unknown option '%s'", name);
 }
 
@@ -686,8 +736,8 @@ int tb200_circ_spectrum(tb200_handle_t h, void* out, void* stream) {
     if (!out) return set_error(TB200_BAD_ARG, "out is NULL");
     cudaStream_t s = (cudaStream_t)stream;
     const int l1 = h->two_level ? h->log2l1 : 0;
-    if (h->prec) k_unscramble<double><<<ew_grid(h->Np), 256, 0, s>>>((cx<double>*)out, (const cx<double>*)h->spec->p, h->Np, l1, h->log2l2);
-    else k_unscramble<float><<<ew_grid(h->Np), 256, 0, s>>>((cx<float>*)out, (const cx<float>*)h->spec->p, h->Np, l1, h->log2l2);
+    if (h->prec) k_unscramble<double><<<ew_grid(h->Np), 256, 0, s>>>((cx<double>*)out, (const cx<double>*)h->spec->p, h->Np, l1, h->log2l2, le_of<double>());
+    else k_unscramble<float><<<ew_grid(h->Np), 256, 0, s>>>((cx<float>*)out, (const cx<float>*)h->spec->p, h->Np, l1, h->log2l2, le_of<float>());
     count_launch();
     return cuda_status(cudaGetLastError(), "k_unscramble");
 }

@@ -7,6 +7,9 @@ namespace tb {
     case 808: return launch_cols_one<double, 8, 8, LAST>(a, s);                    \
     case 908: return launch_cols_one<double, 9, 8, LAST>(a, s);                    \
     case 1008: return launch_cols_one<double, 10, 8, LAST>(a, s);                  \
+    case 1004: return launch_cols_one<double, 10, 4, LAST>(a, s);                  \
+    case 904: return launch_cols_one<double, 9, 4, LAST>(a, s);                    \
+    case 1108: return launch_cols_one<double, 11, 8, LAST>(a, s);                  \
     case 1104: return launch_cols_one<double, 11, 4, LAST>(a, s);                  \
     default: return cudaErrorInvalidValue;                                         \
     }

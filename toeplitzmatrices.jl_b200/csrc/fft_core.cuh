@@ -19,8 +19,15 @@
 
 namespace tb {
 
-constexpr int LOGE = 4;          // 16 points per thread
-constexpr int E = 1 << LOGE;
+// Points per thread (log2): Float64 uses radix-8 threads (32 data registers, so two 512-thread
+// CTAs = 32 warps fit an SM at 64 registers/thread), Float32 radix-16 threads.
+#ifndef TB_LE_F64
+#define TB_LE_F64 3
+#endif
+#ifndef TB_LE_F32
+#define TB_LE_F32 4
+#endif
+template <typename R> __host__ __device__ constexpr int le_of() { return sizeof(R) == 8 ? TB_LE_F64 : TB_LE_F32; }
 constexpr int MAX_LOG2L = 14;    // longest single-pass FFT (16384 points, Float32 only)
 
 template <typename R> struct CxT;
@@ -53,19 +60,20 @@ __host__ __device__ constexpr int brev(int x, int bits) {
 }
 __host__ __device__ constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
 
-// Per-length stage twiddle table: stage k (stride s = L/16^(k+1) > 1) owns the block
-//   T[off_k + (c-1)*s + r] = exp(-2 pi i r c / (16 s)),  c = 1..15, r = 0..s-1
+// Per-length stage twiddle table (E = 2^le points per thread): stage k (stride
+// s = L/E^(k+1) > 1) owns the block
+//   T[off_k + (c-1)*s + r] = exp(-2 pi i r c / (E s)),  c = 1..E-1, r = 0..s-1
 // so a warp reads consecutive entries (thread order) and late stages touch only a few
 // hundred bytes that stay in L1.
-__host__ __device__ constexpr int stage_tw_off(int log2l, int k) {
+__host__ __device__ constexpr int stage_tw_off(int log2l, int k, int le) {
     int off = 0;
     for (int kk = 0; kk < k; ++kk) {
-        int ls = log2l - LOGE * (kk + 1);
-        if (ls > 0) off += (E - 1) << ls;
+        int ls = log2l - le * (kk + 1);
+        if (ls > 0) off += ((1 << le) - 1) << ls;
     }
     return off;
 }
-__host__ __device__ constexpr int stage_tw_total(int log2l) { return stage_tw_off(log2l, log2l / LOGE); }
+__host__ __device__ constexpr int stage_tw_total(int log2l, int le) { return stage_tw_off(log2l, log2l / le, le); }
 
 // d * exp(-/+ 2 pi i k/16); k is a compile-time constant after unrolling.
 template <typename R, bool INV>
@@ -119,24 +127,57 @@ __device__ __forceinline__ void dit_regs(cx<R>* a) {
     }
 }
 
-// Bank-conflict-free swizzles for the contiguous ("row") layout.
-template <typename R> __device__ __forceinline__ int swz(int i);
-template <> __device__ __forceinline__ int swz<double>(int i) { return i ^ (((i >> 3) ^ (i >> 4)) & 7); }
-template <> __device__ __forceinline__ int swz<float>(int i) { return i ^ ((i >> 4) & 15); }
+// Bank-conflict-free XOR swizzles for the contiguous ("row") layout: address = i ^ f(i).
+// f is linear over XOR, and inside a stage an element index is base | (c << ls) with
+// disjoint bits, so address = (base ^ f(base)) ^ ((c << ls) ^ f(c << ls)): one per-thread
+// term plus a compile-time constant per element (a plain immediate offset when f(c << ls) == 0).
+template <typename R> __host__ __device__ constexpr int swz_f(int i);
+template <> __host__ __device__ constexpr int swz_f<double>(int i) { return ((i >> 3) ^ (i >> 4)) & 7; }
+template <> __host__ __device__ constexpr int swz_f<float>(int i) { return (i >> 4) & 15; }
 
 template <typename R> struct RowMap {       // one FFT contiguous in shared memory
-    __device__ __forceinline__ int operator()(int i) const { return swz<R>(i); }
+    __device__ __forceinline__ int pre(int base) const { return base ^ swz_f<R>(base); }
+    __device__ __forceinline__ int at(int pre_, int off) const {
+        constexpr int FIELD = sizeof(R) == 8 ? 7 : 15;     // bits the swizzle may flip
+        return (swz_f<R>(off) == 0 && (off & FIELD) == 0) ? pre_ + off : pre_ ^ (off ^ swz_f<R>(off));
+    }
 };
 template <int TA> struct ColMap {           // TA FFTs interleaved element-wise
     int q;
-    __device__ __forceinline__ int operator()(int i) const { return i * TA + q; }
+    __device__ __forceinline__ int pre(int base) const { return base * TA + q; }
+    __device__ __forceinline__ int at(int pre_, int off) const { return pre_ + off * TA; }
 };
 
 template <typename R> __device__ __forceinline__ cx<R> ldg_cx(const cx<R>* p) { return __ldg(p); }
 
-// One L-point FFT held by NT threads (t = 0..NT-1), 16 registers each.
-template <typename R, int LOG2L>
+// Streaming loads that do not allocate in L1, so the only L1-resident global data are the
+// stage twiddle tables (re-read by every row a CTA processes).
+__device__ __forceinline__ double2 ld_stream(const double2* p) {
+    double2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float2 ld_stream(const float2* p) {
+    float2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double ld_stream(const double* p) {
+    double r;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+    float r;
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+// One L-point FFT held by NT threads (t = 0..NT-1), E = 2^LE complex registers each.
+template <typename R, int LOG2L, int LE = le_of<R>()>
 struct SlotFFT {
+    static constexpr int LOGE = LE;
+    static constexpr int E = 1 << LE;
     static_assert(LOG2L >= LOGE, "FFT shorter than the per-thread radix");
     static constexpr int L = 1 << LOG2L;
     static constexpr int NT = L / E;
@@ -169,32 +210,36 @@ struct SlotFFT {
             const int ls = LOG2L - LOGE * (k + 1);       // log2 of the stride
             const int s = 1 << ls;
             const int g = t >> ls, r = t & (s - 1);
-            const int base = (g << (ls + LOGE)) + r;
+            const int pre = map.pre((g << (ls + LOGE)) + r);
             if (k > 0) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) a[c] = sm[map(base + c * s)];
+                for (int c = 0; c < E; ++c) a[c] = sm[map.at(pre, c << ls)];
             }
             dif_regs<R, E>(a);
             if (ls > 0) {
 #pragma unroll
                 for (int c = 1; c < E; ++c) {
-                    cx<R> w = ldg_cx<R>(tw + (stage_tw_off(LOG2L, k) + (c - 1) * s + r));
+#ifdef TB_EXP_NO_TW
+                    cx<R> w = ldg_cx<R>(tw + (c & 1));
+#else
+                    cx<R> w = ldg_cx<R>(tw + (stage_tw_off(LOG2L, k, LOGE) + (c - 1) * s + r));
+#endif
                     a[brev(c, LOGE)] = cmul(a[brev(c, LOGE)], w);
                 }
             }
             const bool last = (k == NFULL - 1) && (REM == 0);
             if (!last) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) sm[map(base + c * s)] = a[brev(c, LOGE)];
+                for (int c = 0; c < E; ++c) sm[map.at(pre, c << ls)] = a[brev(c, LOGE)];
                 __syncthreads();
             }
         }
         if (REM > 0) {
 #pragma unroll
             for (int u = 0; u < E / RR; ++u) {
-                const int b = t + u * NT;
+                const int pre = map.pre((t + u * NT) * RR);
 #pragma unroll
-                for (int c = 0; c < RR; ++c) a[u * RR + c] = sm[map(b * RR + c)];
+                for (int c = 0; c < RR; ++c) a[u * RR + c] = sm[map.at(pre, c)];
             }
 #pragma unroll
             for (int u = 0; u < E / RR; ++u) dif_regs<R, RR>(a + u * RR);
@@ -210,9 +255,9 @@ struct SlotFFT {
             for (int u = 0; u < E / RR; ++u) dit_regs<R, RR>(a + u * RR);
 #pragma unroll
             for (int u = 0; u < E / RR; ++u) {
-                const int b = t + u * NT;
+                const int pre = map.pre((t + u * NT) * RR);
 #pragma unroll
-                for (int c = 0; c < RR; ++c) sm[map(b * RR + c)] = a[u * RR + c];
+                for (int c = 0; c < RR; ++c) sm[map.at(pre, c)] = a[u * RR + c];
             }
             __syncthreads();
         }
@@ -221,23 +266,27 @@ struct SlotFFT {
             const int ls = LOG2L - LOGE * (k + 1);
             const int s = 1 << ls;
             const int g = t >> ls, r = t & (s - 1);
-            const int base = (g << (ls + LOGE)) + r;
+            const int pre = map.pre((g << (ls + LOGE)) + r);
             const bool first = (k == NFULL - 1) && (REM == 0);
             if (!first) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) a[brev(c, LOGE)] = sm[map(base + c * s)];
+                for (int c = 0; c < E; ++c) a[brev(c, LOGE)] = sm[map.at(pre, c << ls)];
             }
             if (ls > 0) {
 #pragma unroll
                 for (int c = 1; c < E; ++c) {
-                    cx<R> w = ldg_cx<R>(tw + (stage_tw_off(LOG2L, k) + (c - 1) * s + r));
+#ifdef TB_EXP_NO_TW
+                    cx<R> w = ldg_cx<R>(tw + (c & 1));
+#else
+                    cx<R> w = ldg_cx<R>(tw + (stage_tw_off(LOG2L, k, LOGE) + (c - 1) * s + r));
+#endif
                     a[brev(c, LOGE)] = cmulc(a[brev(c, LOGE)], w);
                 }
             }
             dit_regs<R, E>(a);
             if (k > 0) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) sm[map(base + c * s)] = a[c];
+                for (int c = 0; c < E; ++c) sm[map.at(pre, c << ls)] = a[c];
                 __syncthreads();
             }
         }
@@ -247,15 +296,18 @@ struct SlotFFT {
 // Runtime versions of the layout maps (for the un-scramble kernel and the host).
 struct PlanDims {
     int log2l;   // FFT length of this level
+    int LOGE;    // log2 of the points per thread
     __host__ __device__ int L() const { return 1 << log2l; }
-    __host__ __device__ int NT() const { return (1 << log2l) / E; }
+    __host__ __device__ int NT() const { return (1 << log2l) >> LOGE; }
     __host__ __device__ int nfull() const { return log2l / LOGE; }
     __host__ __device__ int rem() const { return log2l % LOGE; }
     __host__ __device__ int pos_of_reg(int i, int t) const {
+        const int E = 1 << LOGE;
         int rm = rem(), rr = 1 << rm;
         return rm == 0 ? t * E + brev(i, LOGE) : (t + (i / rr) * NT()) * rr + brev(i % rr, rm);
     }
     __host__ __device__ int freq_of_pos(int P) const {
+        const int E = 1 << LOGE;
         int k = 0, mult = 1;
         for (int s = 0; s < nfull(); ++s) {
             k += ((P >> (log2l - LOGE * (s + 1))) & (E - 1)) * mult;
@@ -266,6 +318,7 @@ struct PlanDims {
     }
     // inverse maps
     __host__ __device__ int pos_of_freq(int k) const {
+        const int E = 1 << LOGE;
         int P = 0;
         for (int s = 0; s < nfull(); ++s) {
             P |= (k & (E - 1)) << (log2l - LOGE * (s + 1));
@@ -276,6 +329,7 @@ struct PlanDims {
     }
     // spectrum-layout offset (i*NT + t) of position P
     __host__ __device__ int layout_of_pos(int P) const {
+        const int E = 1 << LOGE;
         int rm = rem(), rr = 1 << rm, nt = NT();
         if (rm == 0) {
             int t = P >> LOGE, c = P & (E - 1);

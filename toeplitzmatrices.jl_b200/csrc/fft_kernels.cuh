@@ -39,63 +39,79 @@ struct ConvArgs {
     const cx<R>* tw_lo; const cx<R>* tw_hi; int tw_hb;   // w_Np^m = lo[m & mask] * hi[m >> hb]
 };
 
-// ---- element load / store with the embedding, packing and epilogue fused ---------------
+// ---- per-slot input / output views: the embedding (zero pad, Hankel reversal), the packing of
+// ---- two real columns as re + i*im, and the alpha/beta/real-part epilogue are fused here ----
 template <typename R>
-__device__ __forceinline__ cx<R> load_elem(const void* x, long long ldx, int mode, long long f, long long idx,
-                                           long long n_in, int rev, long long ncols) {
-    if (idx >= n_in) return mk<R>(0, 0);
-    const long long src = rev ? (n_in - 1 - idx) : idx;
-    if (mode == IO_CPLX) return __ldg(reinterpret_cast<const cx<R>*>(x) + f * ldx + src);
-    if (mode == IO_REAL) return mk<R>(__ldg(reinterpret_cast<const R*>(x) + f * ldx + src), 0);
-    // IO_PAIR: columns 2f, 2f+1
-    const R* p = reinterpret_cast<const R*>(x) + (2 * f) * ldx + src;
-    R re = __ldg(p);
-    R im = (2 * f + 1 < ncols) ? __ldg(p + ldx) : (R)0;
-    return mk<R>(re, im);
-}
-
-template <typename R>
-__device__ __forceinline__ void store_elem(const ConvArgs<R>& p, long long f, long long idx, cx<R> v) {
-    if (idx >= p.m_out) return;
-    v.x *= p.scale; v.y *= p.scale;
-    if (p.y_mode == IO_CPLX) {
-        cx<R>* q = reinterpret_cast<cx<R>*>(p.y) + f * p.ldy + idx;
-        cx<R> o = cmul(p.alpha, v);
-        if (p.has_beta) { cx<R> b = cmul(p.beta, *q); o.x += b.x; o.y += b.y; }
-        *q = o;
-    } else if (p.y_mode == IO_REAL) {
-        R* q = reinterpret_cast<R*>(p.y) + f * p.ldy + idx;
-        R o = p.alpha.x * v.x;
-        if (p.has_beta) o = fma(p.beta.x, *q, o);
-        *q = o;
-    } else {  // IO_PAIR
-        R* q = reinterpret_cast<R*>(p.y) + (2 * f) * p.ldy + idx;
-        R o0 = p.alpha.x * v.x;
-        if (p.has_beta) o0 = fma(p.beta.x, *q, o0);
-        *q = o0;
-        if (2 * f + 1 < p.ncols) {
-            R o1 = p.alpha.x * v.y;
-            if (p.has_beta) o1 = fma(p.beta.x, q[p.ldy], o1);
-            q[p.ldy] = o1;
+struct InView {
+    const R* re; const R* im; const cx<R>* c; int mode; int n_in; int rev;
+    __device__ __forceinline__ InView(const ConvArgs<R>& p, long long f) {
+        mode = p.x_mode; n_in = (int)p.n_in; rev = p.reverse_x;
+        re = nullptr; im = nullptr; c = nullptr;
+        if (mode == IO_CPLX) c = reinterpret_cast<const cx<R>*>(p.x) + f * p.ldx;
+        else if (mode == IO_REAL) re = reinterpret_cast<const R*>(p.x) + f * p.ldx;
+        else if (mode == IO_PAIR) {
+            re = reinterpret_cast<const R*>(p.x) + (2 * f) * p.ldx;
+            im = (2 * f + 1 < p.ncols) ? re + p.ldx : nullptr;
         }
     }
-}
+    __device__ __forceinline__ cx<R> load(int idx) const {
+        if (idx >= n_in) return mk<R>(0, 0);
+        const int src = rev ? (n_in - 1 - idx) : idx;
+        if (mode == IO_CPLX) return ld_stream(c + src);
+        const R a = ld_stream(re + src);
+        const R b = im ? ld_stream(im + src) : (R)0;
+        return mk<R>(a, b);
+    }
+};
 
-// ---- contiguous transforms -------------------------------------------------------------
+template <typename R>
+struct OutView {
+    R* re; R* im; cx<R>* c; int mode; int m_out; int has_beta; R scale; cx<R> alpha, beta;
+    __device__ __forceinline__ OutView(const ConvArgs<R>& p, long long f) {
+        mode = p.y_mode; m_out = (int)p.m_out; has_beta = p.has_beta; scale = p.scale; alpha = p.alpha; beta = p.beta;
+        re = nullptr; im = nullptr; c = nullptr;
+        if (mode == IO_CPLX) c = reinterpret_cast<cx<R>*>(p.y) + f * p.ldy;
+        else if (mode == IO_REAL) re = reinterpret_cast<R*>(p.y) + f * p.ldy;
+        else if (mode == IO_PAIR) {
+            re = reinterpret_cast<R*>(p.y) + (2 * f) * p.ldy;
+            im = (2 * f + 1 < p.ncols) ? re + p.ldy : nullptr;
+        }
+    }
+    __device__ __forceinline__ void store(int idx, cx<R> v) const {
+        if (idx >= m_out) return;
+        v.x *= scale; v.y *= scale;
+        if (mode == IO_CPLX) {
+            cx<R> o = cmul(alpha, v);
+            if (has_beta) { const cx<R> b = cmul(beta, c[idx]); o.x += b.x; o.y += b.y; }
+            c[idx] = o;
+        } else {
+            R o0 = alpha.x * v.x;
+            if (has_beta) o0 = fma(beta.x, re[idx], o0);
+            re[idx] = o0;
+            if (im) {
+                R o1 = alpha.x * v.y;
+                if (has_beta) o1 = fma(beta.x, im[idx], o1);
+                im[idx] = o1;
+            }
+        }
+    }
+};
+
 // occupancy target: 128 registers/thread for Float64, 64 for Float32, limited by shared memory
 template <typename R>
 constexpr int min_ctas(int threads, int smem_bytes) {
-    int by_regs = 65536 / (threads * (sizeof(R) == 8 ? 128 : 64));
+    int by_regs = 65536 / (threads * 2 * ((sizeof(R) == 8 ? 4 : 2) << le_of<R>()));   // budget: 2x the data registers
     int by_smem = (220 * 1024) / (smem_bytes > 0 ? smem_bytes : 1);
     int m = by_regs < by_smem ? by_regs : by_smem;
     return m < 1 ? 1 : m;
 }
 
+// ---- contiguous transforms -------------------------------------------------------------
 template <typename R, int LOG2L, int TS>
-__global__ void __launch_bounds__((1 << LOG2L) / E * TS, min_ctas<R>((1 << LOG2L) / E * TS, (int)sizeof(cx<R>) * (1 << LOG2L) * TS))
+__global__ void __launch_bounds__((1 << (LOG2L - le_of<R>())) * TS, min_ctas<R>((1 << (LOG2L - le_of<R>())) * TS, (int)sizeof(cx<R>) * (1 << LOG2L) * TS))
 k_rows(const ConvArgs<R> p) {
     using F = SlotFFT<R, LOG2L>;
-    constexpr int L = F::L, NT = F::NT;
+    constexpr int L = F::L, NT = F::NT, E = F::E;
     extern __shared__ __align__(16) unsigned char smraw[];
     const int slot = threadIdx.x / NT, t = threadIdx.x % NT;
     cx<R>* sm = reinterpret_cast<cx<R>*>(smraw) + slot * L;
@@ -106,29 +122,35 @@ k_rows(const ConvArgs<R> p) {
         const bool live = f < p.nfft;
         const long long fc = live ? f : 0;          // dead slots run on slot 0's data, never store
         cx<R> a[E];
-        const cx<R>* srow = p.spec ? p.spec + (fc % p.spec_rows) * (long long)L : nullptr;
+        const cx<R>* srow = p.spec ? p.spec + (fc % p.spec_rows) * (long long)L + t : nullptr;
         if (p.x_mode == IO_SPEC) {
+            const cx<R>* xin = reinterpret_cast<const cx<R>*>(p.x) + fc * (long long)L + t;
 #pragma unroll
-            for (int i = 0; i < E; ++i) a[i] = __ldg(reinterpret_cast<const cx<R>*>(p.x) + fc * (long long)L + i * NT + t);
+            for (int i = 0; i < E; ++i) a[i] = ld_stream(xin + i * NT);
         } else {
+            const InView<R> in(p, fc);
 #pragma unroll
-            for (int c = 0; c < E; ++c)
-                a[c] = load_elem<R>(p.x, p.ldx, p.x_mode, fc, t + c * NT, p.n_in, p.reverse_x, p.ncols);
+            for (int c = 0; c < E; ++c) a[c] = in.load(t + c * NT);
         }
         if (p.do_fwd) F::forward(a, t, sm, map, p.tw);
         if (srow) {
 #pragma unroll
-            for (int i = 0; i < E; ++i) a[i] = cmul(a[i], __ldg(srow + i * NT + t));
+#ifdef TB_EXP_NO_SPEC
+            for (int i = 0; i < E; ++i) a[i] = cmul(a[i], ld_stream(srow + (i & 1)));
+#else
+            for (int i = 0; i < E; ++i) a[i] = cmul(a[i], ld_stream(srow + i * NT));
+#endif
         }
         if (p.do_inv) F::inverse(a, t, sm, map, p.tw);
         if (live) {
             if (p.y_mode == IO_SPEC) {
-                cx<R>* o = reinterpret_cast<cx<R>*>(p.y) + f * (long long)L;
+                cx<R>* o = reinterpret_cast<cx<R>*>(p.y) + f * (long long)L + t;
 #pragma unroll
-                for (int i = 0; i < E; ++i) o[i * NT + t] = a[i];
+                for (int i = 0; i < E; ++i) o[i * NT] = a[i];
             } else {
+                const OutView<R> out(p, f);
 #pragma unroll
-                for (int j = 0; j < E; ++j) store_elem<R>(p, f, t + j * NT, a[j]);
+                for (int j = 0; j < E; ++j) out.store(t + j * NT, a[j]);
             }
         }
         __syncthreads();
@@ -137,66 +159,71 @@ k_rows(const ConvArgs<R> p) {
 
 // ---- two-level, strided passes -----------------------------------------------------------
 template <typename R>
-__device__ __forceinline__ cx<R> level_twiddle(const ConvArgs<R>& p, long long m) {
-    const cx<R> lo = __ldg(p.tw_lo + (m & ((1LL << p.tw_hb) - 1)));
+__device__ __forceinline__ cx<R> level_twiddle(const ConvArgs<R>& p, unsigned m) {
+#ifdef TB_EXP_NO_LEVEL_TW
+    return __ldg(p.tw_lo + (m & 1u));
+#else
+    const cx<R> lo = __ldg(p.tw_lo + (m & ((1u << p.tw_hb) - 1u)));
     const cx<R> hi = __ldg(p.tw_hi + (m >> p.tw_hb));
     return cmul(lo, hi);
+#endif
 }
 
 // grid.x = (N2/TA) * nfft ; block = TA * NT1
 template <typename R, int LOG2L1, int TA>
-__global__ void __launch_bounds__((1 << LOG2L1) / E * TA, min_ctas<R>((1 << LOG2L1) / E * TA, (int)sizeof(cx<R>) * (1 << LOG2L1) * TA))
+__global__ void __launch_bounds__((1 << (LOG2L1 - le_of<R>())) * TA, min_ctas<R>((1 << (LOG2L1 - le_of<R>())) * TA, (int)sizeof(cx<R>) * (1 << LOG2L1) * TA))
 k_colsA(const ConvArgs<R> p) {
     using F = SlotFFT<R, LOG2L1>;
-    constexpr int NT = F::NT;
+    constexpr int NT = F::NT, E = F::E;
     extern __shared__ __align__(16) unsigned char smraw[];
     cx<R>* sm = reinterpret_cast<cx<R>*>(smraw);
     const int q = threadIdx.x % TA, t = threadIdx.x / TA;
-    const long long N2 = 1LL << p.log2n2;
-    const long long tiles = N2 / TA;
+    const int l2 = p.log2n2;
+    const unsigned tiles = (1u << l2) / TA;
     const long long f = blockIdx.x / tiles;
-    const long long j2 = (blockIdx.x % tiles) * TA + q;
+    const int j2 = (int)(blockIdx.x % tiles) * TA + q;
     ColMap<TA> map{q};
     cx<R> a[E];
+    {
+        const InView<R> in(p, f);
 #pragma unroll
-    for (int c = 0; c < E; ++c) {
-        const long long idx = (long long)(t + c * NT) * N2 + j2;
-        a[c] = load_elem<R>(p.x, p.ldx, p.x_mode, f, idx, p.n_in, p.reverse_x, p.ncols);
+        for (int c = 0; c < E; ++c) a[c] = in.load(((t + c * NT) << l2) + j2);
     }
     F::forward(a, t, sm, map, p.tw);
-    cx<R>* out = p.scratch + f * (N2 << LOG2L1);
+    cx<R>* out = p.scratch + (f << (l2 + LOG2L1)) + j2;
 #pragma unroll
     for (int i = 0; i < E; ++i) {
         const int P = F::pos_of_reg(i, t);
-        const long long k1 = F::freq_of_pos(P);
-        out[(long long)P * N2 + j2] = cmul(a[i], level_twiddle<R>(p, k1 * j2));
+        const unsigned k1 = (unsigned)F::freq_of_pos(P);
+        out[(long long)P << l2] = cmul(a[i], level_twiddle<R>(p, k1 * (unsigned)j2));
     }
 }
 
 template <typename R, int LOG2L1, int TA>
-__global__ void __launch_bounds__((1 << LOG2L1) / E * TA, min_ctas<R>((1 << LOG2L1) / E * TA, (int)sizeof(cx<R>) * (1 << LOG2L1) * TA))
+__global__ void __launch_bounds__((1 << (LOG2L1 - le_of<R>())) * TA, min_ctas<R>((1 << (LOG2L1 - le_of<R>())) * TA, (int)sizeof(cx<R>) * (1 << LOG2L1) * TA))
 k_colsC(const ConvArgs<R> p) {
     using F = SlotFFT<R, LOG2L1>;
-    constexpr int NT = F::NT;
+    constexpr int NT = F::NT, E = F::E;
     extern __shared__ __align__(16) unsigned char smraw[];
     cx<R>* sm = reinterpret_cast<cx<R>*>(smraw);
     const int q = threadIdx.x % TA, t = threadIdx.x / TA;
-    const long long N2 = 1LL << p.log2n2;
-    const long long tiles = N2 / TA;
+    const int l2 = p.log2n2;
+    const unsigned tiles = (1u << l2) / TA;
     const long long f = blockIdx.x / tiles;
-    const long long j2 = (blockIdx.x % tiles) * TA + q;
+    const int j2 = (int)(blockIdx.x % tiles) * TA + q;
     ColMap<TA> map{q};
-    const cx<R>* in = p.scratch + f * (N2 << LOG2L1);
+    const cx<R>* in = p.scratch + (f << (l2 + LOG2L1)) + j2;
     cx<R> a[E];
 #pragma unroll
     for (int i = 0; i < E; ++i) {
         const int P = F::pos_of_reg(i, t);
-        const long long k1 = F::freq_of_pos(P);
-        a[i] = cmulc(in[(long long)P * N2 + j2], level_twiddle<R>(p, k1 * j2));
+        const unsigned k1 = (unsigned)F::freq_of_pos(P);
+        a[i] = cmulc(ld_stream(in + ((long long)P << l2)), level_twiddle<R>(p, k1 * (unsigned)j2));
     }
     F::inverse(a, t, sm, map, p.tw);
+    const OutView<R> out(p, f);
 #pragma unroll
-    for (int j = 0; j < E; ++j) store_elem<R>(p, f, (long long)(t + j * NT) * N2 + j2, a[j]);
+    for (int j = 0; j < E; ++j) out.store(((t + j * NT) << l2) + j2, a[j]);
 }
 
 }  // namespace tb

@@ -6,7 +6,9 @@
 namespace tb {
 
 // slots per CTA for the contiguous kernel: keep >= 128 threads per CTA
-constexpr int rows_ts(int log2l) { return log2l >= 11 ? 1 : (1 << (11 - log2l)); }
+template <typename R> constexpr int rows_ts(int log2l) {
+    return (log2l - le_of<R>()) >= 7 ? 1 : (1 << (7 - (log2l - le_of<R>())));
+}
 
 template <typename R> cudaError_t launch_rows(int log2l, const ConvArgs<R>& a, int num_sms, cudaStream_t s);
 template <typename R> cudaError_t launch_colsA(int log2l1, int ta, const ConvArgs<R>& a, cudaStream_t s);
@@ -14,8 +16,8 @@ template <typename R> cudaError_t launch_colsC(int log2l1, int ta, const ConvArg
 
 template <typename R, int LOG2L>
 cudaError_t launch_rows_one(const ConvArgs<R>& a, int num_sms, cudaStream_t s) {
-    constexpr int TS = rows_ts(LOG2L);
-    constexpr int threads = ((1 << LOG2L) / E) * TS;
+    constexpr int TS = rows_ts<R>(LOG2L);
+    constexpr int threads = (1 << (LOG2L - le_of<R>())) * TS;
     constexpr size_t smem = sizeof(cx<R>) * (size_t)(1 << LOG2L) * TS;
     auto kern = k_rows<R, LOG2L, TS>;
     static bool configured = false;
@@ -34,7 +36,7 @@ cudaError_t launch_rows_one(const ConvArgs<R>& a, int num_sms, cudaStream_t s) {
 
 template <typename R, int LOG2L1, int TA, bool LAST>
 cudaError_t launch_cols_one(const ConvArgs<R>& a, cudaStream_t s) {
-    constexpr int threads = ((1 << LOG2L1) / E) * TA;
+    constexpr int threads = (1 << (LOG2L1 - le_of<R>())) * TA;
     constexpr size_t smem = sizeof(cx<R>) * (size_t)(1 << LOG2L1) * TA;
     auto kern = LAST ? k_colsC<R, LOG2L1, TA> : k_colsA<R, LOG2L1, TA>;
     static bool configured = false;
