@@ -193,7 +193,7 @@ def run_ours(args):
     if args.group_mb:
         tb.set_option("group_bytes", args.group_mb << 20)
     if args.no_overlap:
-        tb.set_option("overlap_streams", 0)
+        tb.set_option("overlap_streams", 1)
     for kv in args.opt:
         k, v = kv.split("=")
         tb.set_option(k, int(v))

@@ -1,0 +1,138 @@
+"""BASELINE.json configurations at (or near) full size: size-independent properties over the whole
+batch plus oracle parity on sampled columns/systems.  Tolerances: 1e-12 (Float64), 1e-5 (Float32)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import toeplitz_oracle as O
+from oracle import build_oracle as OC
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tb():
+    import toeplitz_b200 as tb
+    return tb
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel())
+
+
+def trel(a, b):
+    return float(torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b))
+
+
+def test_c2_batched_toeplitz_f64(tb):
+    """Config 2: Toeplitz{Float64} n = 2^20 x 1024 columns (256 here to bound test memory/time):
+    sampled columns vs the oracle incl. shard edges, linearity over the whole batch, odd column count."""
+    n, l = 1 << 20, 256
+    k = np.arange(n, dtype=np.float64)
+    vc, vr = 0.9 ** k, 0.4 ** k
+    A = tb.Toeplitz(torch.from_numpy(vc).cuda(), torch.from_numpy(vr).cuda())
+    F = tb.factorize(A)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    X = torch.randn((l, n), dtype=torch.float64, device="cuda", generator=g).t()
+    Y = tb.colmajor(n, l)
+    tb.mul_(Y, F, X)
+    Fo = O.factorize(O.Toeplitz(vc, vr))
+    for j in (0, 1, 127, 128, 254, 255):
+        yo = O.mul_factorization(np.zeros(n), Fo, X[:, j].cpu().numpy())
+        assert rel(Y[:, j].cpu().numpy(), yo) <= 1e-12
+    # linearity: A*(X[:, :128] + 2 X[:, 128:]) == Y[:, :128] + 2 Y[:, 128:]
+    Z = tb.colmajor(n, 128)
+    tb.mul_(Z, F, (X[:, :128] + 2 * X[:, 128:]).t().contiguous().t())
+    assert trel(Z, Y[:, :128] + 2 * Y[:, 128:]) <= 1e-12
+    # odd column count + alpha/beta on a strided (ld > n) view
+    Y3 = Y[:, :3].clone().t().contiguous().t()
+    tb.mul_(Y3, F, X[:, 5:8], 2.0, -1.0)
+    assert trel(Y3, 2 * Y[:, 5:8] - Y[:, :3]) <= 1e-12
+
+
+def test_c3_circulant_c64(tb):
+    """Config 3: Circulant{ComplexF64} n = 2^22: factorize, eigvals, ldiv! over RHS columns, inv."""
+    n, l = 1 << 22, 16
+    v = (0.9 ** np.arange(n)).astype(np.complex128)
+    C = tb.Circulant(torch.from_numpy(v).cuda())
+    F = tb.factorize(C)
+    lam = tb.eigvals(F)
+    lam_o = np.fft.fft(v)
+    assert rel(lam.cpu().numpy(), lam_o) <= 1e-12
+    g = torch.Generator(device="cuda").manual_seed(2)
+    B = torch.randn((l, n), dtype=torch.complex128, device="cuda", generator=g).t()
+    X = B.clone()
+    tb.ldiv_(F, X)
+    for j in (0, l - 1):
+        xo = np.fft.ifft(np.fft.fft(B[:, j].cpu().numpy()) / lam_o)
+        assert rel(X[:, j].cpu().numpy(), xo) <= 1e-12
+    # round trip: C * (C \ B) == B over the whole batch
+    R = tb.mul(F, X)
+    assert trel(R, B) <= 1e-12
+    Ci = tb.inv(C)
+    assert rel(Ci.vc.cpu().numpy(), np.fft.ifft(1.0 / lam_o)) <= 1e-11
+
+
+def test_c4_levinson_durbin_many_systems(tb):
+    """Config 4: SymmetricToeplitz{Float64} n = 512, 2*10^5 independent systems (10^6 in bench):
+    sampled systems vs the C oracle, permutation invariance of the batch."""
+    n, nsys = 512, 200000
+    g = torch.Generator(device="cuda").manual_seed(3)
+    R = (torch.rand((nsys, n), dtype=torch.float64, device="cuda", generator=g) / n).t()
+    B = torch.randn((nsys, n), dtype=torch.float64, device="cuda", generator=g).t()
+    X = tb.colmajor(n, nsys)
+    tb.levinson_(X, R[: n - 1, :], B)
+    Yd = tb.durbin(R)
+    idx = [0, 1, 31, 32, 77777, nsys - 1]
+    Rs = np.asfortranarray(R[:, idx].cpu().numpy())
+    Bs = np.asfortranarray(B[:, idx].cpu().numpy())
+    assert rel(X[:, idx].cpu().numpy(), OC.c_levinson_batched(np.asfortranarray(Rs[: n - 1]), Bs)) <= 1e-12
+    assert rel(Yd[:, idx].cpu().numpy(), OC.c_durbin_batched(Rs)) <= 1e-12
+    perm = torch.randperm(nsys, device="cuda", generator=g)[:4096]
+    Xp = tb.colmajor(n, 4096)
+    tb.levinson_(Xp, R[: n - 1, perm].t().contiguous().t(), B[:, perm].t().contiguous().t())
+    assert torch.equal(Xp, X[:, perm])
+    # KMS set (well conditioned): r_k = rho^k
+    rho = 0.1 + 0.8 * torch.rand(1000, dtype=torch.float64, device="cuda", generator=g)
+    Rk = (rho[None, :] ** torch.arange(1, n, dtype=torch.float64, device="cuda")[:, None]).t().contiguous().t()
+    Bk = B[:, :1000].t().contiguous().t()
+    Xk = tb.colmajor(n, 1000)
+    tb.levinson_(Xk, Rk, Bk)
+    assert rel(Xk.cpu().numpy(), OC.c_levinson_batched(np.asfortranarray(Rk.cpu().numpy()), np.asfortranarray(Bk.cpu().numpy()))) <= 1e-11
+
+
+def test_c5a_hankel_c32(tb):
+    """Config 5a: Hankel{ComplexF32} n = 2^24 matvec (embedding 2^25, two-level Float32 plan)."""
+    n = 1 << 24
+    rng = np.random.default_rng(5)
+    v = ((rng.standard_normal(2 * n - 1) + 1j * rng.standard_normal(2 * n - 1)) / np.sqrt(2)).astype(np.complex64)
+    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) / np.sqrt(2)).astype(np.complex64)
+    H = tb.Hankel(torch.from_numpy(v).cuda(), (n, n))
+    y = tb.mul(H, torch.from_numpy(x).cuda())
+    # oracle in double precision on the same Float32 inputs (reference path would run in ComplexF32)
+    yo = O.matvec(O.Hankel(v.astype(np.complex128), (n, n)), x.astype(np.complex128))
+    assert rel(y.cpu().numpy(), yo) <= 1e-5
+
+
+def test_c5b_cgs_strang_c32(tb):
+    """Config 5b: SymmetricToeplitz cgs + Strang in ComplexF32.  Oracle parity at n = 2^20 for a fixed
+    iteration count; at n = 2^24 the returned residual must match a recomputed ||b - A x||/||b||."""
+    for n, check_oracle in ((1 << 20, True), (1 << 24, False)):
+        v = (0.5 ** np.arange(n)).astype(np.complex64)
+        rng = np.random.default_rng(7)
+        b = rng.standard_normal(n).astype(np.complex64)
+        A = tb.SymmetricToeplitz(torch.from_numpy(v).cuda())
+        M = tb.factorize(tb.strang(A))
+        bd = torch.from_numpy(b).cuda()
+        x, err, it, flag = tb.cgs(A, torch.zeros_like(bd), bd, M, 4, 0.0)
+        assert (it, flag) == (4, 1)
+        r = bd - tb.mul(A, x)
+        err2 = float(torch.linalg.vector_norm(r) / torch.linalg.vector_norm(bd))
+        assert abs(err - err2) <= 1e-5 * max(1.0, err2) + 1e-6
+        assert err2 < 1e-4
+        if check_oracle:
+            Ao = O.SymmetricToeplitz(v)
+            xo, eo, ito, fo = O.cgs(Ao, np.zeros(n, np.complex64), b.copy(), O.factorize(O.strang(Ao)), 4, 0.0)
+            assert (ito, fo) == (it, flag)
+            assert rel(x.cpu().numpy(), xo) <= 1e-4

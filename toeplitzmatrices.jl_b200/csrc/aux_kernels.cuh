@@ -138,6 +138,60 @@ __global__ void k_unscramble(cx<R>* __restrict__ out, const cx<R>* __restrict__ 
     }
 }
 
+// ---- Bluestein (chirp-z) glue for Circulants whose size is not a power of two ------------------
+// DFT_n(x)[k] = c[k] * sum_j T[k-j] (c[j] x[j]),  c[j] = exp(-i pi j^2/n),  T[d] = conj(c[d]):
+// a symmetric-Toeplitz product, done by the same FFT-convolution kernels.  These kernels are the
+// O(n) diagonal scalings around it.  (needed by factorize(strang(A)) at any n.)
+template <typename R>
+__global__ void k_bs_pre(cx<R>* __restrict__ u, long long ldu, const void* x, long long ldx, int x_cplx, int conj_x,
+                         const cx<R>* __restrict__ chirp, long long n, long long ncols) {
+    const long long total = n * ncols;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long col = e / n, j = e - col * n;
+        cx<R> v = x_cplx ? reinterpret_cast<const cx<R>*>(x)[col * ldx + j]
+                         : mk<R>(reinterpret_cast<const R*>(x)[col * ldx + j], 0);
+        if (conj_x) v.y = -v.y;
+        u[col * ldu + j] = cmul(chirp[j], v);
+    }
+}
+// u2 = chirp .* conj((chirp .* v) .* spec)   -- spectrum multiply + hand-over to the inverse transform
+template <typename R>
+__global__ void k_bs_mid(cx<R>* __restrict__ u2, const cx<R>* __restrict__ v, long long ld, const cx<R>* __restrict__ chirp,
+                         const cx<R>* __restrict__ spec, long long n, long long ncols) {
+    const long long total = n * ncols;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long col = e / n, j = e - col * n;
+        cx<R> X = cmul(cmul(chirp[j], v[col * ld + j]), spec[j]);
+        X.y = -X.y;
+        u2[col * ld + j] = cmul(chirp[j], X);
+    }
+}
+// y = alpha * maybereal(scale * (conj_out ? conj(chirp .* v) : chirp .* v)) + beta * y
+template <typename R>
+__global__ void k_bs_post(void* y, long long ldy, int y_cplx, const cx<R>* __restrict__ v, long long ldv,
+                          const cx<R>* __restrict__ chirp, long long n, long long ncols, R scale, int conj_out,
+                          int take_real, cx<R> alpha, cx<R> beta, int has_beta) {
+    const long long total = n * ncols;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long col = e / n, j = e - col * n;
+        cx<R> t = cmul(chirp[j], v[col * ldv + j]);
+        if (conj_out) t.y = -t.y;
+        t.x *= scale; t.y *= scale;
+        if (take_real) t.y = 0;
+        if (y_cplx) {
+            cx<R>* q = reinterpret_cast<cx<R>*>(y) + col * ldy + j;
+            cx<R> o = cmul(alpha, t);
+            if (has_beta) { const cx<R> b = cmul(beta, *q); o.x += b.x; o.y += b.y; }
+            *q = o;
+        } else {
+            R* q = reinterpret_cast<R*>(y) + col * ldy + j;
+            R o = alpha.x * t.x;
+            if (has_beta) o = fma(beta.x, *q, o);
+            *q = o;
+        }
+    }
+}
+
 // strang / chan (src/linearalgebra.jl:255-274), elementwise on device.
 template <typename R>
 __global__ void k_strang_chan(void* vout, int which, int kind, const void* vc, const void* vr, int a_cplx, long long n) {

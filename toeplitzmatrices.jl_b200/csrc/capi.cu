@@ -28,7 +28,7 @@ static std::atomic<long long> g_launches{0};
 static std::atomic<long long> g_group_bytes{48ll << 20};   // two-level scratch budget per group
 static std::atomic<long long> g_host_chunk_bytes{256ll << 20};
 static std::atomic<int> g_time_passes{0};
-static std::atomic<int> g_overlap_streams{1};
+static std::atomic<int> g_overlap_streams{2};   // helper streams for group overlap (0/1 = off)
 static std::atomic<int> g_l2max_f64{12}, g_l2max_f32{13}, g_ta_cap{0};   // plan tuning knobs
 
 // optional per-pass device timing (bench.py's roofline leg): CUDA events recorded on the
@@ -192,15 +192,20 @@ struct tb200_fact {
     int64_t m = 0, n = 0, Np = 0;
     int log2np = 0, two_level = 0, log2l1 = 0, log2l2 = 0, ta = 0;
     int reverse_x = 0;
-    std::shared_ptr<DevBuf> spec, inv_spec, tw_lo, tw_hi, scratch, scratch2;
+    static constexpr int MAXS = 4;
+    std::shared_ptr<DevBuf> spec, inv_spec, tw_lo, tw_hi, scratch, scratch_extra[MAXS];
     int tw_hb = 0;
     bool spec_valid = false;
+    // Bluestein plan (Circulant, n not a power of two): spectrum kept in NATURAL order (n entries)
+    bool bluestein = false;
+    std::shared_ptr<tb200_fact> bs_conv;          // complex symmetric Toeplitz T[d] = exp(+i pi d^2/n)
+    std::shared_ptr<DevBuf> bs_chirp, bs_u, bs_v; // chirp c[j] = exp(-i pi j^2/n); work buffers
     // two helper streams: consecutive column groups of a two-level product alternate between them so
     // the tail of one pass overlaps the next group's passes (each stream owns one workspace)
-    cudaStream_t hs[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaStream_t hs[MAXS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAXS] = {nullptr, nullptr, nullptr, nullptr};
     ~tb200_fact() {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < MAXS; ++i) {
             if (hs[i]) cudaStreamDestroy(hs[i]);
             if (ev_join[i]) cudaEventDestroy(ev_join[i]);
         }
@@ -301,26 +306,30 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     long long G = std::max(1ll, g_group_bytes.load() / (long long)(Np * sizeof(cx<R>)));
     G = std::min(G, c.nfft);
     TB_TRY(ensure_scratch(h, (size_t)G * Np * sizeof(cx<R>)));
-    const bool overlap = g_overlap_streams.load() && c.nfft > G && c.do_fwd && c.do_inv;
-    cx<R>* scratch_of[2] = {reinterpret_cast<cx<R>*>(h->scratch->p), reinterpret_cast<cx<R>*>(h->scratch->p)};
-    cudaStream_t stream_of[2] = {s, s};
+    const int NSTR = g_overlap_streams.load();
+    const bool overlap = NSTR >= 2 && c.nfft > G && c.do_fwd && c.do_inv;
+    const int nstr = overlap ? NSTR : 1;
+    cx<R>* scratch_of[tb200_fact::MAXS];
+    cudaStream_t stream_of[tb200_fact::MAXS];
+    for (int i = 0; i < tb200_fact::MAXS; ++i) { scratch_of[i] = reinterpret_cast<cx<R>*>(h->scratch->p); stream_of[i] = s; }
     if (overlap) {
-        if (!h->scratch2 || h->scratch2->bytes < (size_t)G * Np * sizeof(cx<R>)) {
-            h->scratch2.reset();
-            TB_TRY(dev_alloc(h->scratch2, (size_t)G * Np * sizeof(cx<R>), "second workspace"));
+        for (int i = 1; i < nstr; ++i) {
+            if (!h->scratch_extra[i] || h->scratch_extra[i]->bytes < (size_t)G * Np * sizeof(cx<R>)) {
+                h->scratch_extra[i].reset();
+                TB_TRY(dev_alloc(h->scratch_extra[i], (size_t)G * Np * sizeof(cx<R>), "extra workspace"));
+            }
+            scratch_of[i] = reinterpret_cast<cx<R>*>(h->scratch_extra[i]->p);
         }
-        if (!h->hs[0]) {
-            for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < nstr; ++i) {
+            if (!h->hs[i]) {
                 TB_CUDA(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking), "helper stream");
                 TB_CUDA(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming), "event");
             }
-            TB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), "event");
+            stream_of[i] = h->hs[i];
         }
-        scratch_of[1] = reinterpret_cast<cx<R>*>(h->scratch2->p);
-        stream_of[0] = h->hs[0]; stream_of[1] = h->hs[1];
+        if (!h->ev_fork) TB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), "event");
         TB_CUDA(cudaEventRecord(h->ev_fork, s), "fork");
-        TB_CUDA(cudaStreamWaitEvent(h->hs[0], h->ev_fork, 0), "fork");
-        TB_CUDA(cudaStreamWaitEvent(h->hs[1], h->ev_fork, 0), "fork");
+        for (int i = 0; i < nstr; ++i) TB_CUDA(cudaStreamWaitEvent(h->hs[i], h->ev_fork, 0), "fork");
     }
     cudaStream_t user_stream = s;
     a.log2n2 = h->log2l2;
@@ -333,8 +342,8 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     long long group_index = 0;
     for (long long f0 = 0; f0 < c.nfft; f0 += G, ++group_index) {
         const long long g = std::min(G, c.nfft - f0);
-        cx<R>* scratch = scratch_of[group_index & 1];
-        s = stream_of[group_index & 1];
+        cx<R>* scratch = scratch_of[group_index % nstr];
+        s = stream_of[group_index % nstr];
         a.scratch = scratch;
         // pass A
         if (c.do_fwd) {
@@ -382,7 +391,7 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
         }
     }
     if (overlap) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < nstr; ++i) {
             TB_CUDA(cudaEventRecord(h->ev_join[i], h->hs[i]), "join");
             TB_CUDA(cudaStreamWaitEvent(user_stream, h->ev_join[i], 0), "join");
         }
@@ -416,16 +425,18 @@ static int new_handle(int kind, int dtype, int64_t m, int64_t n, tb200_fact** ou
     h->m = m; h->n = n;
     TB_CUDA(cudaGetDevice(&h->device), "cudaGetDevice");
     if (kind == TB200_CIRCULANT) {
-        if ((n & (n - 1)) != 0)
-            return set_error(TB200_UNSUPPORTED,
-                             "Circulant of size %lld: only power-of-two sizes are implemented (Bluestein is SURVEY 8f)", (long long)n);
         h->Np = n;
+        if ((n & (n - 1)) != 0 || n < 16) {       // exact n-point DFT semantics through a chirp-z plan
+            h->bluestein = true;
+            h->reverse_x = 0;
+            TB_TRY(dev_alloc(h->spec, (size_t)n * (h->prec ? 16 : 8), "spectrum"));
+            *out = h.release();
+            return TB200_OK;
+        }
     } else {
         h->Np = 1ll << next_log2(m + n - 1);
     }
     if (h->Np < 16) h->Np = 16;
-    if (kind == TB200_CIRCULANT && h->Np != n)
-        return set_error(TB200_UNSUPPORTED, "Circulant of size %lld < 16: use tb200_mul_direct / dense algebra", (long long)n);
     h->log2np = next_log2(h->Np);
     h->reverse_x = (kind == TB200_HANKEL);
     TB_TRY(make_plan(h.get()));
@@ -452,6 +463,97 @@ static int factorize_t(tb200_fact* h, const void* vc, const void* vr, cudaStream
 }
 
 static int mode_for(bool cplx) { return cplx ? IO_CPLX : IO_REAL; }
+
+// ---------------------------------------------------------------------------------------
+// Bluestein plan: exact n-point DFTs for Circulants of any size on top of the pow2 kernels
+// ---------------------------------------------------------------------------------------
+template <typename R>
+static int bs_setup_t(tb200_fact* h, cudaStream_t s) {
+    const int64_t n = h->n;
+    std::vector<cx<R>> c((size_t)n), cc((size_t)n);
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for (int64_t j = 0; j < n; ++j) {
+        const long long q = (long long)((j * j) % (2 * n));          // exact: j^2 < 2^50
+        const long double ang = pi * (long double)q / (long double)n;
+        c[(size_t)j] = mk<R>((R)cosl(ang), (R)(-sinl(ang)));
+        cc[(size_t)j] = mk<R>((R)cosl(ang), (R)sinl(ang));
+    }
+    TB_TRY(dev_alloc(h->bs_chirp, sizeof(cx<R>) * (size_t)n, "chirp"));
+    TB_CUDA(cudaMemcpyAsync(h->bs_chirp->p, c.data(), sizeof(cx<R>) * (size_t)n, cudaMemcpyHostToDevice, s), "chirp upload");
+    std::shared_ptr<DevBuf> tvc;
+    TB_TRY(dev_alloc(tvc, sizeof(cx<R>) * (size_t)n, "chirp filter"));
+    TB_CUDA(cudaMemcpyAsync(tvc->p, cc.data(), sizeof(cx<R>) * (size_t)n, cudaMemcpyHostToDevice, s), "chirp filter upload");
+    tb200_fact* t = nullptr;
+    TB_TRY(new_handle(TB200_SYMMETRIC, h->prec ? TB200_C64 : TB200_C32, n, n, &t));
+    h->bs_conv.reset(t);
+    TB_TRY(factorize_t<R>(t, tvc->p, nullptr, s));
+    TB_CUDA(cudaStreamSynchronize(s), "bluestein setup sync");           // host staging vectors go out of scope
+    return TB200_OK;
+}
+
+template <typename R>
+static int bs_conv_t(tb200_fact* h, cx<R>* v, const cx<R>* u, int64_t ld, int64_t ncols, cudaStream_t s) {
+    tb200_fact* t = h->bs_conv.get();
+    ConvCall c;
+    c.x = u; c.ldx = ld; c.x_mode = IO_CPLX; c.n_in = h->n;
+    c.y = v; c.ldy = ld; c.y_mode = IO_CPLX; c.m_out = h->n;
+    c.ncols = ncols; c.nfft = ncols; c.spec = t->spec->p;
+    c.scale = 1.0 / (double)t->Np;
+    return run_conv_t<R>(t, c, s);
+}
+
+// y = alpha * maybereal(OP(x)) + beta*y with OP = forward DFT (mode 0), inverse DFT (mode 1, x is a
+// natural-order spectrum) or circulant apply ifft(fft(x) .* spec) (mode 2), column by column chunk.
+template <typename R>
+static int bs_run_t(tb200_fact* h, int mode, const void* spec, void* y, int64_t ldy, int y_cplx, int take_real,
+                    const void* x, int64_t ldx, int x_cplx, int64_t ncols, const double alpha[2], const double beta[2],
+                    cudaStream_t s) {
+    const int64_t n = h->n;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncols, (64ll << 20) / (int64_t)(n * sizeof(cx<R>))));
+    const size_t wbytes = (size_t)chunk * n * sizeof(cx<R>);
+    if (!h->bs_u || h->bs_u->bytes < wbytes) { h->bs_u.reset(); TB_TRY(dev_alloc(h->bs_u, wbytes, "bluestein workspace")); }
+    if (!h->bs_v || h->bs_v->bytes < wbytes) { h->bs_v.reset(); TB_TRY(dev_alloc(h->bs_v, wbytes, "bluestein workspace")); }
+    cx<R>* u = (cx<R>*)h->bs_u->p; cx<R>* v = (cx<R>*)h->bs_v->p;
+    const cx<R>* chirp = (const cx<R>*)h->bs_chirp->p;
+    const cx<R> al = mk<R>((R)(alpha ? alpha[0] : 1.0), (R)(alpha ? alpha[1] : 0.0));
+    const cx<R> be = mk<R>((R)(beta ? beta[0] : 0.0), (R)(beta ? beta[1] : 0.0));
+    const int has_beta = (be.x != 0 || be.y != 0);
+    const size_t xsz = x_cplx ? sizeof(cx<R>) : sizeof(R), ysz = y_cplx ? sizeof(cx<R>) : sizeof(R);
+    for (int64_t c0 = 0; c0 < ncols; c0 += chunk) {
+        const int64_t nc = std::min(chunk, ncols - c0);
+        const void* xs = (const char*)x + (size_t)c0 * ldx * xsz;
+        void* ys = (char*)y + (size_t)c0 * ldy * ysz;
+        const unsigned grid = ew_grid(n * nc);
+        k_bs_pre<R><<<grid, 256, 0, s>>>(u, n, xs, ldx, x_cplx, mode == 1, chirp, n, nc);
+        count_launch();
+        TB_TRY(bs_conv_t<R>(h, v, u, n, nc, s));
+        if (mode == 2) {
+            k_bs_mid<R><<<grid, 256, 0, s>>>(u, v, n, chirp, (const cx<R>*)spec, n, nc);
+            count_launch();
+            TB_TRY(bs_conv_t<R>(h, v, u, n, nc, s));
+        }
+        const int inv = (mode != 0);
+        k_bs_post<R><<<grid, 256, 0, s>>>(ys, ldy, y_cplx, v, n, chirp, n, nc, inv ? (R)(1.0 / (double)n) : (R)1, inv,
+                                          take_real, al, be, has_beta);
+        count_launch();
+        TB_CUDA(cudaGetLastError(), "bluestein kernels");
+    }
+    return TB200_OK;
+}
+
+static int bs_run(tb200_fact* h, int mode, const void* spec, void* y, int64_t ldy, int y_cplx, int take_real, const void* x,
+                  int64_t ldx, int x_cplx, int64_t ncols, const double alpha[2], const double beta[2], cudaStream_t s) {
+    return h->prec ? bs_run_t<double>(h, mode, spec, y, ldy, y_cplx, take_real, x, ldx, x_cplx, ncols, alpha, beta, s)
+                   : bs_run_t<float>(h, mode, spec, y, ldy, y_cplx, take_real, x, ldx, x_cplx, ncols, alpha, beta, s);
+}
+
+// factorize for a Bluestein Circulant: spectrum = DFT_n(vc), natural order
+static int bs_factorize(tb200_fact* h, const void* vc, cudaStream_t s) {
+    TB_TRY(h->prec ? bs_setup_t<double>(h, s) : bs_setup_t<float>(h, s));
+    TB_TRY(bs_run(h, 0, nullptr, h->spec->p, h->n, 1, 0, vc, h->n, !h->a_real, 1, nullptr, nullptr, s));
+    h->spec_valid = true;
+    return TB200_OK;
+}
 
 }  // namespace tb
 
@@ -482,7 +584,7 @@ int tb200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "group_bytes")) { g_group_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "host_chunk_bytes")) { g_host_chunk_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "time_passes")) { g_time_passes = value ? 1 : 0; return TB200_OK; }
-    if (!strcmp(name, "overlap_streams")) { g_overlap_streams = value ? 1 : 0; return TB200_OK; }
+    if (!strcmp(name, "overlap_streams")) { g_overlap_streams = (int)std::min<int64_t>(std::max<int64_t>(value, 0), tb200_fact::MAXS); return TB200_OK; }
     if (!strcmp(name, "l2max_f64")) { g_l2max_f64 = (int)value; return TB200_OK; }
     if (!strcmp(name, "l2max_f32")) { g_l2max_f32 = (int)value; return TB200_OK; }
     if (!strcmp(name, "ta_cap")) { g_ta_cap = (int)value; return TB200_OK; }
@@ -495,6 +597,10 @@ int tb200_factorize_empty(int kind, int dtype, int64_t m, int64_t n, void* strea
     TB_TRY(check_factorize_args(kind, dtype, m, n, nullptr, nullptr, false));
     tb200_fact* h = nullptr;
     TB_TRY(new_handle(kind, dtype, m, n, &h));
+    if (h->bluestein) {
+        int st = h->prec ? bs_setup_t<double>(h, (cudaStream_t)stream) : bs_setup_t<float>(h, (cudaStream_t)stream);
+        if (st != TB200_OK) { delete h; return st; }
+    }
     h->spec_valid = true;          // the caller fills the spectrum buffer (broadcast)
     *out = h;
     return TB200_OK;
@@ -506,7 +612,8 @@ int tb200_factorize(int kind, int dtype, int64_t m, int64_t n, const void* vc, c
     TB_TRY(check_factorize_args(kind, dtype, m, n, vc, vr, true));
     tb200_fact* h = nullptr;
     TB_TRY(new_handle(kind, dtype, m, n, &h));
-    int st = h->prec ? factorize_t<double>(h, vc, vr, (cudaStream_t)stream) : factorize_t<float>(h, vc, vr, (cudaStream_t)stream);
+    int st = h->bluestein ? bs_factorize(h, vc, (cudaStream_t)stream)
+           : h->prec ? factorize_t<double>(h, vc, vr, (cudaStream_t)stream) : factorize_t<float>(h, vc, vr, (cudaStream_t)stream);
     if (st != TB200_OK) { delete h; return st; }
     *out = h;
     return TB200_OK;
@@ -567,6 +674,11 @@ static int mul_impl(tb200_fact* h, const void* spec, bool is_ldiv, void* y, int6
         return set_error(TB200_DIM_MISMATCH, "leading dimensions (%lld, %lld) smaller than the matrix size %lldx%lld",
                          (long long)ldy, (long long)ldx, (long long)h->m, (long long)h->n);
     const bool xc = dt_is_cplx(xdtype), yc = dt_is_cplx(ydtype);
+    if (h->bluestein) {
+        if (!yc && (!h->a_real || (!is_ldiv && (xc || (alpha && alpha[1] != 0.0) || (beta && beta[1] != 0.0)))))
+            return set_error(TB200_BAD_ARG, "a real y requires a real matrix, real x and real alpha/beta (InexactError in the reference)");
+        return bs_run(h, 2, spec, y, ldy, yc, 0, x, ldx, xc, ncols, alpha, beta, s);
+    }
     ConvCall c;
     c.x = x; c.ldx = ldx; c.n_in = h->n; c.reverse_x = h->reverse_x;
     c.y = y; c.ldy = ldy; c.m_out = h->m;
@@ -735,6 +847,8 @@ int tb200_circ_spectrum(tb200_handle_t h, void* out, void* stream) {
     TB_TRY(require_circulant(h));
     if (!out) return set_error(TB200_BAD_ARG, "out is NULL");
     cudaStream_t s = (cudaStream_t)stream;
+    if (h->bluestein)
+        return cuda_status(cudaMemcpyAsync(out, h->spec->p, (size_t)h->n * (h->prec ? 16 : 8), cudaMemcpyDeviceToDevice, s), "spectrum copy");
     const int l1 = h->two_level ? h->log2l1 : 0;
     if (h->prec) k_unscramble<double><<<ew_grid(h->Np), 256, 0, s>>>((cx<double>*)out, (const cx<double>*)h->spec->p, h->Np, l1, h->log2l2, le_of<double>());
     else k_unscramble<float><<<ew_grid(h->Np), 256, 0, s>>>((cx<float>*)out, (const cx<float>*)h->spec->p, h->Np, l1, h->log2l2, le_of<float>());
@@ -745,6 +859,7 @@ int tb200_circ_spectrum(tb200_handle_t h, void* out, void* stream) {
 static int clone_plan(tb200_fact* h, tb200_fact** out) {
     tb200_fact* g = nullptr;
     TB_TRY(new_handle(h->kind, h->dtype, h->m, h->n, &g));
+    if (h->bluestein) { g->bs_conv = h->bs_conv; g->bs_chirp = h->bs_chirp; }
     *out = g;
     return TB200_OK;
 }
@@ -775,6 +890,7 @@ int tb200_circ_mul(tb200_handle_t a, tb200_handle_t b, void* stream, tb200_handl
     tb200_fact* g = nullptr;
     const int dt = (dt_is_cplx(a->dtype) || dt_is_cplx(b->dtype)) ? (a->prec ? TB200_C64 : TB200_C32) : a->dtype;
     TB_TRY(new_handle(TB200_CIRCULANT, dt, a->n, a->n, &g));
+    if (a->bluestein) { g->bs_conv = a->bs_conv; g->bs_chirp = a->bs_chirp; }
     cudaStream_t s = (cudaStream_t)stream;
     if (a->prec) k_spec_mul<double><<<ew_grid(a->Np), 256, 0, s>>>((cx<double>*)g->spec->p, (const cx<double>*)a->spec->p, (const cx<double>*)b->spec->p, a->Np);
     else k_spec_mul<float><<<ew_grid(a->Np), 256, 0, s>>>((cx<float>*)g->spec->p, (const cx<float>*)a->spec->p, (const cx<float>*)b->spec->p, a->Np);
@@ -790,6 +906,8 @@ int tb200_circ_to_vc(tb200_handle_t h, void* vc_out, int out_dtype, void* stream
     TB_TRY(require_circulant(h));
     if (!vc_out) return set_error(TB200_BAD_ARG, "vc_out is NULL");
     if (!dt_valid(out_dtype) || dt_prec(out_dtype) != h->prec) return set_error(TB200_BAD_ARG, "output dtype must have the factorization's precision");
+    if (h->bluestein)
+        return bs_run(h, 1, nullptr, vc_out, h->n, dt_is_cplx(out_dtype), 0, h->spec->p, h->n, 1, 1, nullptr, nullptr, (cudaStream_t)stream);
     ConvCall c;
     c.x = h->spec->p; c.ldx = h->Np; c.x_mode = IO_SPEC; c.n_in = h->Np;
     c.y = vc_out; c.ldy = h->Np; c.y_mode = dt_is_cplx(out_dtype) ? IO_CPLX : IO_REAL; c.m_out = h->n;
