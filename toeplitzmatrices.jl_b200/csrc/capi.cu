@@ -81,15 +81,37 @@ static inline int dt_prec(int dt) { return (dt == TB200_F64 || dt == TB200_C64) 
 static inline size_t dt_size(int dt) { return (dt_prec(dt) ? 8 : 4) * (dt_is_cplx(dt) ? 2 : 1); }
 static inline bool dt_valid(int dt) { return dt >= 0 && dt <= 3; }
 
+// Device memory comes from the stream-ordered allocator on one private stream per device, with the
+// pool's release threshold raised so that factorize/destroy cycles (the reference re-factorizes on
+// every vector mul!, src/linearalgebra.jl:37) reuse cached blocks instead of paying cudaMalloc/cudaFree.
+static cudaStream_t alloc_stream() {
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (!streams[dev]) {
+        cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
+    return streams[dev];
+}
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
+    cudaStream_t st = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
 };
 static int dev_alloc(std::shared_ptr<DevBuf>& out, size_t bytes, const char* what) {
     auto b = std::make_shared<DevBuf>();
     if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMalloc(&b->p, bytes);
+    b->st = alloc_stream();
+    cudaError_t e = cudaMallocAsync(&b->p, bytes, b->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->st);       // the block is usable from any stream afterwards
     if (e != cudaSuccess) { b->p = nullptr; return cuda_status(e, what); }
     b->bytes = bytes;
     out = b;
@@ -240,25 +262,36 @@ static int make_plan(tb200_fact* h) {
     while (ta > 4 && ((size_t)1 << l1) * ta * esz > 128 * 1024) ta >>= 1;
     if (g_ta_cap.load() >= 4 && ta > g_ta_cap.load()) ta = g_ta_cap.load();
     h->two_level = 1; h->log2l1 = l1; h->log2l2 = l2; h->ta = ta;
-    // inter-level twiddles  w_Np^m = lo[m & mask] * hi[m >> hb]
+    // inter-level twiddles  w_Np^m = lo[m & mask] * hi[m >> hb]  (cached per device / precision / length)
     h->tw_hb = (l + 1) / 2;
     const long long nlo = 1ll << h->tw_hb, nhi = 1ll << (l - h->tw_hb);
-    if (h->prec) {
-        std::vector<cx<double>> lo, hi;
-        fill_twiddles<double>(lo, nlo, 1, 1ll << l);
-        fill_twiddles<double>(hi, nhi, nlo, 1ll << l);
-        TB_TRY(dev_alloc(h->tw_lo, lo.size() * 16, "level twiddles"));
-        TB_TRY(dev_alloc(h->tw_hi, hi.size() * 16, "level twiddles"));
-        TB_CUDA(cudaMemcpy(h->tw_lo->p, lo.data(), lo.size() * 16, cudaMemcpyHostToDevice), "level twiddle upload");
-        TB_CUDA(cudaMemcpy(h->tw_hi->p, hi.data(), hi.size() * 16, cudaMemcpyHostToDevice), "level twiddle upload");
-    } else {
-        std::vector<cx<float>> lo, hi;
-        fill_twiddles<float>(lo, nlo, 1, 1ll << l);
-        fill_twiddles<float>(hi, nhi, nlo, 1ll << l);
-        TB_TRY(dev_alloc(h->tw_lo, lo.size() * 8, "level twiddles"));
-        TB_TRY(dev_alloc(h->tw_hi, hi.size() * 8, "level twiddles"));
-        TB_CUDA(cudaMemcpy(h->tw_lo->p, lo.data(), lo.size() * 8, cudaMemcpyHostToDevice), "level twiddle upload");
-        TB_CUDA(cudaMemcpy(h->tw_hi->p, hi.data(), hi.size() * 8, cudaMemcpyHostToDevice), "level twiddle upload");
+    {
+        static std::mutex mu;
+        static std::shared_ptr<DevBuf> cache[64][2][40][2];
+        std::lock_guard<std::mutex> lock(mu);
+        auto& clo = cache[h->device & 63][h->prec][l][0];
+        auto& chi = cache[h->device & 63][h->prec][l][1];
+        if (!clo || !chi) {
+            if (h->prec) {
+                std::vector<cx<double>> lo, hi;
+                fill_twiddles<double>(lo, nlo, 1, 1ll << l);
+                fill_twiddles<double>(hi, nhi, nlo, 1ll << l);
+                TB_TRY(dev_alloc(clo, lo.size() * 16, "level twiddles"));
+                TB_TRY(dev_alloc(chi, hi.size() * 16, "level twiddles"));
+                TB_CUDA(cudaMemcpy(clo->p, lo.data(), lo.size() * 16, cudaMemcpyHostToDevice), "level twiddle upload");
+                TB_CUDA(cudaMemcpy(chi->p, hi.data(), hi.size() * 16, cudaMemcpyHostToDevice), "level twiddle upload");
+            } else {
+                std::vector<cx<float>> lo, hi;
+                fill_twiddles<float>(lo, nlo, 1, 1ll << l);
+                fill_twiddles<float>(hi, nhi, nlo, 1ll << l);
+                TB_TRY(dev_alloc(clo, lo.size() * 8, "level twiddles"));
+                TB_TRY(dev_alloc(chi, hi.size() * 8, "level twiddles"));
+                TB_CUDA(cudaMemcpy(clo->p, lo.data(), lo.size() * 8, cudaMemcpyHostToDevice), "level twiddle upload");
+                TB_CUDA(cudaMemcpy(chi->p, hi.data(), hi.size() * 8, cudaMemcpyHostToDevice), "level twiddle upload");
+            }
+        }
+        h->tw_lo = clo;
+        h->tw_hi = chi;
     }
     return TB200_OK;
 }
