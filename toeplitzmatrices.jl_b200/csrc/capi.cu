@@ -15,6 +15,7 @@
 
 #include "capi_internal.h"
 #include "fft_launch.cuh"
+#include "mega_kernel.cuh"
 #include "aux_kernels.cuh"
 #include "blas1.cuh"
 
@@ -29,6 +30,7 @@ static std::atomic<long long> g_group_bytes{48ll << 20};   // two-level scratch 
 static std::atomic<long long> g_host_chunk_bytes{256ll << 20};
 static std::atomic<int> g_time_passes{0};
 static std::atomic<int> g_overlap_streams{2};   // helper streams for group overlap (0/1 = off)
+static std::atomic<int> g_mega{0};               // opt-in persistent single-launch path (measured slower than 3 kernels x 2 streams)
 static std::atomic<int> g_l2max_f64{12}, g_l2max_f32{13}, g_ta_cap{0};   // plan tuning knobs
 
 // optional per-pass device timing (bench.py's roofline leg): CUDA events recorded on the
@@ -215,7 +217,7 @@ struct tb200_fact {
     int log2np = 0, two_level = 0, log2l1 = 0, log2l2 = 0, ta = 0;
     int reverse_x = 0;
     static constexpr int MAXS = 4;
-    std::shared_ptr<DevBuf> spec, inv_spec, tw_lo, tw_hi, scratch, scratch_extra[MAXS];
+    std::shared_ptr<DevBuf> spec, inv_spec, tw_lo, tw_hi, scratch, scratch_extra[MAXS], sched;
     int tw_hb = 0;
     bool spec_valid = false;
     // Bluestein plan (Circulant, n not a power of two): spectrum kept in NATURAL order (n entries)
@@ -336,6 +338,34 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     }
     // ---- two-level: A (strided cols, fwd) -> B (rows: fwd * spec inv) -> C (strided cols, inv)
     const long long Np = h->Np, N1 = 1ll << h->log2l1, N2 = 1ll << h->log2l2;
+    if (g_mega.load() && c.do_fwd && c.do_inv && c.nfft >= 2 && c.spec && c.x_mode != IO_SPEC && c.y_mode != IO_SPEC &&
+        mega_supported<R>(h->log2l1, h->log2l2, h->ta) && c.nfft < (1ll << 20)) {
+        // one persistent cooperative launch for the whole batch (mega_kernel.cuh)
+        const size_t wbytes = (size_t)Np * sizeof(cx<R>);
+        TB_TRY(ensure_scratch(h, wbytes));
+        if (!h->scratch_extra[1] || h->scratch_extra[1]->bytes < wbytes) {
+            h->scratch_extra[1].reset();
+            TB_TRY(dev_alloc(h->scratch_extra[1], wbytes, "second workspace"));
+        }
+        const size_t sbytes = sizeof(unsigned) * (size_t)(4 + 3 * c.nfft);
+        if (!h->sched || h->sched->bytes < sbytes) { h->sched.reset(); TB_TRY(dev_alloc(h->sched, sbytes, "tile scheduler state")); }
+        TB_CUDA(cudaMemsetAsync(h->sched->p, 0, sbytes, s), "scheduler reset");
+        MegaArgs<R> ma;
+        a.log2n2 = h->log2l2;
+        a.tw_lo = reinterpret_cast<const cx<R>*>(h->tw_lo->p);
+        a.tw_hi = reinterpret_cast<const cx<R>*>(h->tw_hi->p);
+        a.tw_hb = h->tw_hb;
+        ma.c = a;
+        ma.tw_cols = tw_cols; ma.tw_rows = tw_rows;
+        ma.scratch[0] = reinterpret_cast<cx<R>*>(h->scratch->p);
+        ma.scratch[1] = reinterpret_cast<cx<R>*>(h->scratch_extra[1]->p);
+        ma.ticket = reinterpret_cast<unsigned*>(h->sched->p);
+        ma.done = ma.ticket + 4;
+        ma.npairs = c.nfft;
+        count_launch();
+        PassTimer pt(1, s);
+        return cuda_status(launch_mega<R>(h->log2l1, h->log2l2, h->ta, ma, num_sms(), s), "k_mega");
+    }
     long long G = std::max(1ll, g_group_bytes.load() / (long long)(Np * sizeof(cx<R>)));
     G = std::min(G, c.nfft);
     TB_TRY(ensure_scratch(h, (size_t)G * Np * sizeof(cx<R>)));
@@ -621,6 +651,7 @@ int tb200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "l2max_f64")) { g_l2max_f64 = (int)value; return TB200_OK; }
     if (!strcmp(name, "l2max_f32")) { g_l2max_f32 = (int)value; return TB200_OK; }
     if (!strcmp(name, "ta_cap")) { g_ta_cap = (int)value; return TB200_OK; }
+    if (!strcmp(name, "mega")) { g_mega = value ? 1 : 0; return TB200_OK; }
     return set_error(TB200_BAD_ARG, "unknown option '%s'", name);
 }
 

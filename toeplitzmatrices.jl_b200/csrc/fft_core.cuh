@@ -97,6 +97,9 @@ __device__ __forceinline__ cx<R> mul_w16(cx<R> d, int k) {
 // In-register radix-RAD DIF butterfly: natural in -> a[brev(c)] = X[c].
 template <typename R, int RAD>
 __device__ __forceinline__ void dif_regs(cx<R>* a) {
+#ifdef TB_EXP_NO_BFLY
+    return;
+#endif
 #pragma unroll
     for (int h = RAD / 2; h >= 1; h >>= 1) {
 #pragma unroll
@@ -113,6 +116,9 @@ __device__ __forceinline__ void dif_regs(cx<R>* a) {
 // Mirror: a[brev(c)] = X[c] in -> natural out, conjugate twiddles (unnormalised inverse).
 template <typename R, int RAD>
 __device__ __forceinline__ void dit_regs(cx<R>* a) {
+#ifdef TB_EXP_NO_BFLY
+    return;
+#endif
 #pragma unroll
     for (int h = 1; h <= RAD / 2; h <<= 1) {
 #pragma unroll
@@ -173,6 +179,14 @@ __device__ __forceinline__ float ld_stream(const float* p) {
     return r;
 }
 
+#ifdef TB_EXP_NO_SMEM      // timing experiment only: drop the shared-memory traffic (wrong results)
+#define TB_SM_LOAD(dst, src) (void)0
+#define TB_SM_STORE(dst, src) (void)0
+#else
+#define TB_SM_LOAD(dst, src) dst = src
+#define TB_SM_STORE(dst, src) dst = src
+#endif
+
 // One L-point FFT held by NT threads (t = 0..NT-1), E = 2^LE complex registers each.
 template <typename R, int LOG2L, int LE = le_of<R>()>
 struct SlotFFT {
@@ -213,7 +227,7 @@ struct SlotFFT {
             const int pre = map.pre((g << (ls + LOGE)) + r);
             if (k > 0) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) a[c] = sm[map.at(pre, c << ls)];
+                for (int c = 0; c < E; ++c) TB_SM_LOAD(a[c], sm[map.at(pre, c << ls)]);
             }
             dif_regs<R, E>(a);
             if (ls > 0) {
@@ -230,7 +244,7 @@ struct SlotFFT {
             const bool last = (k == NFULL - 1) && (REM == 0);
             if (!last) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) sm[map.at(pre, c << ls)] = a[brev(c, LOGE)];
+                for (int c = 0; c < E; ++c) TB_SM_STORE(sm[map.at(pre, c << ls)], a[brev(c, LOGE)]);
                 __syncthreads();
             }
         }
@@ -239,7 +253,7 @@ struct SlotFFT {
             for (int u = 0; u < E / RR; ++u) {
                 const int pre = map.pre((t + u * NT) * RR);
 #pragma unroll
-                for (int c = 0; c < RR; ++c) a[u * RR + c] = sm[map.at(pre, c)];
+                for (int c = 0; c < RR; ++c) TB_SM_LOAD(a[u * RR + c], sm[map.at(pre, c)]);
             }
 #pragma unroll
             for (int u = 0; u < E / RR; ++u) dif_regs<R, RR>(a + u * RR);
@@ -257,7 +271,7 @@ struct SlotFFT {
             for (int u = 0; u < E / RR; ++u) {
                 const int pre = map.pre((t + u * NT) * RR);
 #pragma unroll
-                for (int c = 0; c < RR; ++c) sm[map.at(pre, c)] = a[u * RR + c];
+                for (int c = 0; c < RR; ++c) TB_SM_STORE(sm[map.at(pre, c)], a[u * RR + c]);
             }
             __syncthreads();
         }
@@ -270,7 +284,7 @@ struct SlotFFT {
             const bool first = (k == NFULL - 1) && (REM == 0);
             if (!first) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) a[brev(c, LOGE)] = sm[map.at(pre, c << ls)];
+                for (int c = 0; c < E; ++c) TB_SM_LOAD(a[brev(c, LOGE)], sm[map.at(pre, c << ls)]);
             }
             if (ls > 0) {
 #pragma unroll
@@ -286,7 +300,7 @@ struct SlotFFT {
             dit_regs<R, E>(a);
             if (k > 0) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) sm[map.at(pre, c << ls)] = a[c];
+                for (int c = 0; c < E; ++c) TB_SM_STORE(sm[map.at(pre, c << ls)], a[c]);
                 __syncthreads();
             }
         }
