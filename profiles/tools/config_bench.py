@@ -100,6 +100,9 @@ def c5():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c1", "c3", "c4", "c5"]
-    for w in which:
+    args = [a for a in sys.argv[1:] if "=" not in a]
+    for kv in (a for a in sys.argv[1:] if "=" in a):       # tuning: library options, e.g. l2max_f64=13
+        k, v = kv.split("=")
+        tb.set_option(k, int(v))
+    for w in (args or ["c1", "c3", "c4", "c5"]):
         globals()[w]()

@@ -28,6 +28,22 @@ __device__ __forceinline__ R warp_sum(R v) {
     return v;
 }
 
+// Fused reduction of two values: after the first exchange lanes 0-15 carry d1 partials and lanes 16-31 d2
+// partials, so the remaining four levels reduce both at once (5 double shuffles instead of 10).
+template <typename R>
+__device__ __forceinline__ void warp_sum2(R& d1, R& d2, int lane) {
+    const bool hi = (lane & 16) != 0;
+    R keep = hi ? d2 : d1, give = hi ? d1 : d2;
+    keep += __shfl_xor_sync(0xffffffffu, give, 16);
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    d1 = __shfl_sync(0xffffffffu, keep, 0);
+    d2 = __shfl_sync(0xffffffffu, keep, 16);
+}
+
+__device__ __forceinline__ double fast_rcp(double x) { return 1.0 / x; }
+__device__ __forceinline__ float fast_rcp(float x) { return 1.0f / x; }
+
 // shift the first SROWS super-rows of v up by one element, inserting `head` at index 0
 template <typename R, int SROWS>
 __device__ __forceinline__ void shift_up(R* v, R head, int lane) {
@@ -66,17 +82,19 @@ __device__ __forceinline__ void run_superrows(LevState<R, S>& st, int n, int lan
                     if (!DURBIN) d1 = fma(st.rh[i], st.x[i], d1);
                     d2 = fma(st.rh[i], st.y[i], d2);
                 }
-                if (!DURBIN) d1 = warp_sum(d1);
-                d2 = warp_sum(d2);
+                if (!DURBIN) warp_sum2(d1, d2, lane);
+                else d2 = warp_sum(d2);
+                // one reciprocal per step instead of the reference's two divisions by beta (<= 1 ulp apart)
+                const R ibeta = fast_rcp(st.beta);
                 if (!DURBIN) {
-                    const R mu = (b_s[k] - d1) / st.beta;
+                    const R mu = (b_s[k] - d1) * ibeta;
 #pragma unroll
                     for (int i = 0; i < ACT; ++i) st.x[i] = fma(mu, st.yh[i], st.x[i]);
                     if (lane == lb) st.x[SC * LB + j] = mu;
                 }
                 if (DURBIN || k < n - 1) {
                     const R rk = r_s[k];
-                    st.alpha = -(rk + d2) / st.beta;
+                    st.alpha = -(rk + d2) * ibeta;
 #pragma unroll
                     for (int i = 0; i < ACT; ++i) {
                         const R yo = st.y[i];
@@ -94,7 +112,7 @@ __device__ __forceinline__ void run_superrows(LevState<R, S>& st, int n, int lan
 }
 
 template <typename R, int S, bool DURBIN>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, DURBIN ? 4 : 3)
 k_levinson_warp(int64_t n64, int64_t nsys, const R* __restrict__ Rm, int64_t ldr, const R* __restrict__ Bm,
                 int64_t ldb, R* __restrict__ Xm, int64_t ldx, const R* __restrict__ diag) {
     constexpr int NREG = S * LB;
