@@ -217,7 +217,7 @@ struct tb200_fact {
     int log2np = 0, two_level = 0, log2l1 = 0, log2l2 = 0, ta = 0;
     int reverse_x = 0;
     static constexpr int MAXS = 4;
-    std::shared_ptr<DevBuf> spec, inv_spec, tw_lo, tw_hi, scratch, scratch_extra[MAXS], sched;
+    std::shared_ptr<DevBuf> spec, inv_spec, tw_lo, tw_hi, tw_g, scratch, scratch_extra[MAXS], sched;
     int tw_hb = 0;
     bool spec_valid = false;
     // Bluestein plan (Circulant, n not a power of two): spectrum kept in NATURAL order (n entries)
@@ -294,6 +294,39 @@ static int make_plan(tb200_fact* h) {
         }
         h->tw_lo = clo;
         h->tw_hi = chi;
+        // [E][N2] table w_Np^(delta_i * j2): delta_i = frequency offset of register i in the strided transform
+        static std::shared_ptr<DevBuf> gcache[64][2][40][16];
+        auto& cg = gcache[h->device & 63][h->prec][l][l1];
+        if (!cg) {
+            const int le = h->prec ? le_of<double>() : le_of<float>();
+            const int Ecount = 1 << le;
+            const long long N2 = 1ll << l2, Npl = 1ll << l;
+            PlanDims d1{l1, le};
+            std::vector<long long> nums((size_t)Ecount * N2);
+            for (int i = 0; i < Ecount; ++i) {
+                const long long delta = d1.freq_of_pos(d1.pos_of_reg(i, 0));
+                for (long long j2 = 0; j2 < N2; ++j2) nums[(size_t)i * N2 + j2] = (delta * j2) % Npl;
+            }
+            const long double twopi = 6.283185307179586476925286766559005768L;
+            if (h->prec) {
+                std::vector<cx<double>> g(nums.size());
+                for (size_t e = 0; e < nums.size(); ++e) {
+                    const long double ang = twopi * (long double)nums[e] / (long double)Npl;
+                    g[e] = mk<double>((double)cosl(ang), (double)(-sinl(ang)));
+                }
+                TB_TRY(dev_alloc(cg, g.size() * 16, "level twiddle table"));
+                TB_CUDA(cudaMemcpy(cg->p, g.data(), g.size() * 16, cudaMemcpyHostToDevice), "level twiddle upload");
+            } else {
+                std::vector<cx<float>> g(nums.size());
+                for (size_t e = 0; e < nums.size(); ++e) {
+                    const long double ang = twopi * (long double)nums[e] / (long double)Npl;
+                    g[e] = mk<float>((float)cosl(ang), (float)(-sinl(ang)));
+                }
+                TB_TRY(dev_alloc(cg, g.size() * 8, "level twiddle table"));
+                TB_CUDA(cudaMemcpy(cg->p, g.data(), g.size() * 8, cudaMemcpyHostToDevice), "level twiddle upload");
+            }
+        }
+        h->tw_g = cg;
     }
     return TB200_OK;
 }
@@ -355,6 +388,7 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
         a.tw_lo = reinterpret_cast<const cx<R>*>(h->tw_lo->p);
         a.tw_hi = reinterpret_cast<const cx<R>*>(h->tw_hi->p);
         a.tw_hb = h->tw_hb;
+        a.tw_g = reinterpret_cast<const cx<R>*>(h->tw_g->p);
         ma.c = a;
         ma.tw_cols = tw_cols; ma.tw_rows = tw_rows;
         ma.scratch[0] = reinterpret_cast<cx<R>*>(h->scratch->p);
@@ -399,6 +433,7 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     a.tw_lo = reinterpret_cast<const cx<R>*>(h->tw_lo->p);
     a.tw_hi = reinterpret_cast<const cx<R>*>(h->tw_hi->p);
     a.tw_hb = h->tw_hb;
+    a.tw_g = reinterpret_cast<const cx<R>*>(h->tw_g->p);
     const size_t in_esz = (c.x_mode == IO_REAL || c.x_mode == IO_PAIR) ? sizeof(R) : sizeof(cx<R>);
     const size_t out_esz = (c.y_mode == IO_REAL || c.y_mode == IO_PAIR) ? sizeof(R) : sizeof(cx<R>);
     const long long cols_per_fft = (c.x_mode == IO_PAIR || c.y_mode == IO_PAIR) ? 2 : 1;

@@ -37,7 +37,13 @@ struct ConvArgs {
     cx<R>* scratch;           // nfft * Np complex
     int log2n2;               // N2 = contiguous (row) length
     const cx<R>* tw_lo; const cx<R>* tw_hi; int tw_hb;   // w_Np^m = lo[m & mask] * hi[m >> hb]
+    const cx<R>* tw_g;        // [E][N2]: w_Np^(delta_i * j2), delta_i = frequency offset of register i (thread-independent)
 };
+
+// Inter-level twiddles of one thread (fixed column j2): w^(k1(i) j2) = w^(kbase(t) j2) * w^(delta_i j2).
+// One split-table lookup for the base, E coalesced loads from the [E][N2] table, E complex multiplies.
+template <typename R, class F>
+__device__ __forceinline__ void level_twiddles(const ConvArgs<R>& p, int t, int j2, cx<R>* w);
 
 // ---- per-slot input / output views: the embedding (zero pad, Hankel reversal), the packing of
 // ---- two real columns as re + i*im, and the alpha/beta/real-part epilogue are fused here ----
@@ -169,6 +175,15 @@ __device__ __forceinline__ cx<R> level_twiddle(const ConvArgs<R>& p, unsigned m)
 #endif
 }
 
+template <typename R, class F>
+__device__ __forceinline__ void level_twiddles(const ConvArgs<R>& p, int t, int j2, cx<R>* w) {
+    const unsigned kbase = (unsigned)F::freq_of_pos(F::pos_of_reg(0, t));
+    const cx<R> base = level_twiddle<R>(p, kbase * (unsigned)j2);
+    const cx<R>* g = p.tw_g + j2;
+#pragma unroll
+    for (int i = 0; i < F::E; ++i) w[i] = cmul(base, __ldg(g + ((long long)i << p.log2n2)));
+}
+
 // grid.x = (N2/TA) * nfft ; block = TA * NT1
 template <typename R, int LOG2L1, int TA>
 __global__ void __launch_bounds__((1 << (LOG2L1 - le_of<R>())) * TA, min_ctas<R>((1 << (LOG2L1 - le_of<R>())) * TA, (int)sizeof(cx<R>) * (1 << LOG2L1) * TA))
@@ -191,12 +206,10 @@ k_colsA(const ConvArgs<R> p) {
     }
     F::forward(a, t, sm, map, p.tw);
     cx<R>* out = p.scratch + (f << (l2 + LOG2L1)) + j2;
+    cx<R> w[E];
+    level_twiddles<R, F>(p, t, j2, w);
 #pragma unroll
-    for (int i = 0; i < E; ++i) {
-        const int P = F::pos_of_reg(i, t);
-        const unsigned k1 = (unsigned)F::freq_of_pos(P);
-        out[(long long)P << l2] = cmul(a[i], level_twiddle<R>(p, k1 * (unsigned)j2));
-    }
+    for (int i = 0; i < E; ++i) out[(long long)F::pos_of_reg(i, t) << l2] = cmul(a[i], w[i]);
 }
 
 template <typename R, int LOG2L1, int TA>
@@ -214,11 +227,11 @@ k_colsC(const ConvArgs<R> p) {
     ColMap<TA> map{q};
     const cx<R>* in = p.scratch + (f << (l2 + LOG2L1)) + j2;
     cx<R> a[E];
+    {
+        cx<R> w[E];
+        level_twiddles<R, F>(p, t, j2, w);
 #pragma unroll
-    for (int i = 0; i < E; ++i) {
-        const int P = F::pos_of_reg(i, t);
-        const unsigned k1 = (unsigned)F::freq_of_pos(P);
-        a[i] = cmulc(ld_stream(in + ((long long)P << l2)), level_twiddle<R>(p, k1 * (unsigned)j2));
+        for (int i = 0; i < E; ++i) a[i] = cmulc(ld_stream(in + ((long long)F::pos_of_reg(i, t) << l2)), w[i]);
     }
     F::inverse(a, t, sm, map, p.tw);
     const OutView<R> out(p, f);

@@ -59,12 +59,10 @@ __device__ __noinline__ void mega_tile_A(const MegaArgs<R>& m, long long i, unsi
     }
     FA::forward(a, t, sm, map, m.tw_cols);
     cx<R>* out = m.scratch[i & 1] + j2;
+    cx<R> w[E];
+    level_twiddles<R, FA>(p, t, j2, w);
 #pragma unroll
-    for (int r = 0; r < E; ++r) {
-        const int Pp = FA::pos_of_reg(r, t);
-        const unsigned k1 = (unsigned)FA::freq_of_pos(Pp);
-        out[(long long)Pp << l2] = cmul(a[r], level_twiddle<R>(p, k1 * (unsigned)j2));
-    }
+    for (int r = 0; r < E; ++r) out[(long long)FA::pos_of_reg(r, t) << l2] = cmul(a[r], w[r]);
 }
 
 template <typename R, int LOG2L1, int LOG2L2, int TA>
@@ -96,11 +94,11 @@ __device__ __noinline__ void mega_tile_C(const MegaArgs<R>& m, long long i, unsi
     ColMap<TA> map{q};
     const cx<R>* in = m.scratch[i & 1] + j2;
     cx<R> a[E];
+    {
+        cx<R> w[E];
+        level_twiddles<R, FA>(p, t, j2, w);
 #pragma unroll
-    for (int r = 0; r < E; ++r) {
-        const int Pp = FA::pos_of_reg(r, t);
-        const unsigned k1 = (unsigned)FA::freq_of_pos(Pp);
-        a[r] = cmulc(ld_cg(in + ((long long)Pp << l2)), level_twiddle<R>(p, k1 * (unsigned)j2));
+        for (int r = 0; r < E; ++r) a[r] = cmulc(ld_cg(in + ((long long)FA::pos_of_reg(r, t) << l2)), w[r]);
     }
     FA::inverse(a, t, sm, map, m.tw_cols);
     const OutView<R> out(p, i);
