@@ -16,6 +16,7 @@
 #include "capi_internal.h"
 #include "fft_launch.cuh"
 #include "mega_kernel.cuh"
+#include "pipe_kernels.cuh"
 #include "aux_kernels.cuh"
 #include "blas1.cuh"
 
@@ -31,6 +32,7 @@ static std::atomic<long long> g_host_chunk_bytes{256ll << 20};
 static std::atomic<int> g_time_passes{0};
 static std::atomic<int> g_overlap_streams{2};   // helper streams for group overlap (0/1 = off)
 static std::atomic<int> g_mega{0};               // opt-in persistent single-launch path (measured slower than 3 kernels x 2 streams)
+static std::atomic<int> g_pipe_b{0};             // opt-in cp.async double-buffered persistent pass B (measured slower)
 static std::atomic<int> g_l2max_f64{12}, g_l2max_f32{13}, g_ta_cap{0};   // plan tuning knobs
 
 // optional per-pass device timing (bench.py's roofline leg): CUDA events recorded on the
@@ -474,6 +476,10 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
             }
             count_launch();
             PassTimer pt(1, s);
+            if (g_pipe_b.load() && c.do_fwd && c.do_inv && c.spec && rowsB_pipe_supported<R>(h->log2l2)) {
+                TB_CUDA(launch_rowsB_pipe<R>(h->log2l2, scratch, g * N1, reinterpret_cast<const cx<R>*>(c.spec), (int)N1,
+                                             tw_rows, num_sms(), s), "k_rowsB_pipe");
+            } else
             TB_CUDA(launch_rows<R>(h->log2l2, pb, num_sms(), s), "k_rows (pass B)");
         }
         // pass C
@@ -687,6 +693,7 @@ int tb200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "l2max_f32")) { g_l2max_f32 = (int)value; return TB200_OK; }
     if (!strcmp(name, "ta_cap")) { g_ta_cap = (int)value; return TB200_OK; }
     if (!strcmp(name, "mega")) { g_mega = value ? 1 : 0; return TB200_OK; }
+    if (!strcmp(name, "pipe_b")) { g_pipe_b = value ? 1 : 0; return TB200_OK; }
     return set_error(TB200_BAD_ARG, "unknown option '%s'", name);
 }
 

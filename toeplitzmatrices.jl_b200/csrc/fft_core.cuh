@@ -19,10 +19,11 @@
 
 namespace tb {
 
-// Points per thread (log2): Float64 uses radix-8 threads (32 data registers, so two 512-thread
-// CTAs = 32 warps fit an SM at 64 registers/thread), Float32 radix-16 threads.
+// Points per thread (log2).  Radix-16 threads for both precisions: fewer shared-memory round trips
+// (the LSU is the tightest resource); radix-8 Float64 threads (64 registers, 32 warps/SM) were measured
+// 4 % slower once the stage twiddles are generated in registers (profiles/experiments_r01.md).
 #ifndef TB_LE_F64
-#define TB_LE_F64 3
+#define TB_LE_F64 4
 #endif
 #ifndef TB_LE_F32
 #define TB_LE_F32 4
@@ -156,6 +157,25 @@ template <int TA> struct ColMap {           // TA FFTs interleaved element-wise
 
 template <typename R> __device__ __forceinline__ cx<R> ldg_cx(const cx<R>* p) { return __ldg(p); }
 
+// Stage twiddles of one thread: w[c] = exp(-2 pi i r c / (E s)), c = 1..E-1.  The load/store unit is the
+// tightest resource of the Float64 transforms (profiles/experiments_r01.md), so for Float64 only w[1] is
+// loaded and the other powers are built by a depth-<=4 product tree in the (less loaded) FP64 pipe;
+// Float32 keeps the full table (accuracy margin, FP32 pipe share).
+#ifndef TB_TWGEN_F64
+#define TB_TWGEN_F64 1
+#endif
+template <typename R, int E>
+__device__ __forceinline__ void stage_twiddles_of_thread(const cx<R>* __restrict__ blk, int s, int r, cx<R>* w) {
+    if constexpr (sizeof(R) == 8 && TB_TWGEN_F64) {
+        w[1] = ldg_cx<R>(blk + r);
+#pragma unroll
+        for (int c = 2; c < E; ++c) w[c] = cmul(w[c / 2], w[c - c / 2]);
+    } else {
+#pragma unroll
+        for (int c = 1; c < E; ++c) w[c] = ldg_cx<R>(blk + (c - 1) * s + r);
+    }
+}
+
 // Streaming loads that do not allocate in L1, so the only L1-resident global data are the
 // stage twiddle tables (re-read by every row a CTA processes).
 __device__ __forceinline__ double2 ld_stream(const double2* p) {
@@ -215,8 +235,9 @@ struct SlotFFT {
         return k;
     }
 
-    // On entry a[c] = x[t + c*NT].  On exit register i holds X[freq_of_pos(pos_of_reg(i,t))].
-    template <class Map>
+    // On entry a[c] = x[t + c*NT] (or, with FROM_SMEM, the natural-order input already sits in shared
+    // memory at sm[map(idx)]).  On exit register i holds X[freq_of_pos(pos_of_reg(i,t))].
+    template <class Map, bool FROM_SMEM = false>
     __device__ __forceinline__ static void forward(cx<R>* a, int t, cx<R>* sm, Map map,
                                                    const cx<R>* __restrict__ tw) {
 #pragma unroll
@@ -225,21 +246,16 @@ struct SlotFFT {
             const int s = 1 << ls;
             const int g = t >> ls, r = t & (s - 1);
             const int pre = map.pre((g << (ls + LOGE)) + r);
-            if (k > 0) {
+            if (k > 0 || FROM_SMEM) {
 #pragma unroll
                 for (int c = 0; c < E; ++c) TB_SM_LOAD(a[c], sm[map.at(pre, c << ls)]);
             }
             dif_regs<R, E>(a);
             if (ls > 0) {
+                cx<R> w[E];
+                stage_twiddles_of_thread<R, E>(tw + stage_tw_off(LOG2L, k, LOGE), s, r, w);
 #pragma unroll
-                for (int c = 1; c < E; ++c) {
-#ifdef TB_EXP_NO_TW
-                    cx<R> w = ldg_cx<R>(tw + (c & 1));
-#else
-                    cx<R> w = ldg_cx<R>(tw + (stage_tw_off(LOG2L, k, LOGE) + (c - 1) * s + r));
-#endif
-                    a[brev(c, LOGE)] = cmul(a[brev(c, LOGE)], w);
-                }
+                for (int c = 1; c < E; ++c) a[brev(c, LOGE)] = cmul(a[brev(c, LOGE)], w[c]);
             }
             const bool last = (k == NFULL - 1) && (REM == 0);
             if (!last) {
@@ -287,15 +303,10 @@ struct SlotFFT {
                 for (int c = 0; c < E; ++c) TB_SM_LOAD(a[brev(c, LOGE)], sm[map.at(pre, c << ls)]);
             }
             if (ls > 0) {
+                cx<R> w[E];
+                stage_twiddles_of_thread<R, E>(tw + stage_tw_off(LOG2L, k, LOGE), s, r, w);
 #pragma unroll
-                for (int c = 1; c < E; ++c) {
-#ifdef TB_EXP_NO_TW
-                    cx<R> w = ldg_cx<R>(tw + (c & 1));
-#else
-                    cx<R> w = ldg_cx<R>(tw + (stage_tw_off(LOG2L, k, LOGE) + (c - 1) * s + r));
-#endif
-                    a[brev(c, LOGE)] = cmulc(a[brev(c, LOGE)], w);
-                }
+                for (int c = 1; c < E; ++c) a[brev(c, LOGE)] = cmulc(a[brev(c, LOGE)], w[c]);
             }
             dit_regs<R, E>(a);
             if (k > 0) {
