@@ -159,14 +159,18 @@ template <typename R> __device__ __forceinline__ cx<R> ldg_cx(const cx<R>* p) { 
 
 // Stage twiddles of one thread: w[c] = exp(-2 pi i r c / (E s)), c = 1..E-1.  The load/store unit is the
 // tightest resource of the Float64 transforms (profiles/experiments_r01.md), so for Float64 only w[1] is
-// loaded and the other powers are built by a depth-<=4 product tree in the (less loaded) FP64 pipe;
-// Float32 keeps the full table (accuracy margin, FP32 pipe share).
+// loaded and the other powers are built by a depth-<=4 product tree in the (less loaded) FMA pipe
+// (about 4 extra roundings per twiddle: ~1e-15 relative in Float64, ~3e-7 in Float32 -- inside the
+// 1e-12 / 1e-5 parity budgets, measured by the GPU parity tests).  TB_TWGEN_*=0 restores full tables.
 #ifndef TB_TWGEN_F64
 #define TB_TWGEN_F64 1
 #endif
+#ifndef TB_TWGEN_F32
+#define TB_TWGEN_F32 1
+#endif
 template <typename R, int E>
 __device__ __forceinline__ void stage_twiddles_of_thread(const cx<R>* __restrict__ blk, int s, int r, cx<R>* w) {
-    if constexpr (sizeof(R) == 8 && TB_TWGEN_F64) {
+    if constexpr ((sizeof(R) == 8 && TB_TWGEN_F64) || (sizeof(R) == 4 && TB_TWGEN_F32)) {
         w[1] = ldg_cx<R>(blk + r);
 #pragma unroll
         for (int c = 2; c < E; ++c) w[c] = cmul(w[c / 2], w[c - c / 2]);
