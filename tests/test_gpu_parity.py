@@ -380,3 +380,57 @@ def test_mul_host_pipeline(tb):
     tb.mul_host_(Yh, F, Xh)
     tb.set_option("host_chunk_bytes", 256 << 20)
     assert rel(Yh.numpy(), O.matvec(O.Toeplitz(vc, vr), X)) <= TOL64
+
+
+def test_bluestein_factorization_products(tb):
+    """mul! through a Circulant *factorization* of non-power-of-two size (chirp-z apply), real and complex,
+    vector and matrix, alpha/beta."""
+    rng = np.random.default_rng(21)
+    for n in (6, 101, 2000):
+        for dtype in (np.float64, np.complex128, np.complex64):
+            v = (rng.random(n) + 0.5).astype(dtype)
+            Co, Cd = O.Circulant(v), tb.Circulant(dev(v))
+            F = tb.factorize(Cd)
+            X = rng.standard_normal((n, 3)).astype(dtype)
+            Y0 = rng.standard_normal((n, 3)).astype(dtype)
+            Yd = devmat(Y0.copy())
+            tb.mul_(Yd, F, devmat(X), 2.0, -0.5)
+            ref = 2.0 * (Co.dense() @ X) - 0.5 * Y0
+            assert rel(host(Yd), ref) <= tol_of(dtype) * 10
+            assert rel(host(tb.mul(F, dev(X[:, 0].copy()))), Co.dense() @ X[:, 0]) <= tol_of(dtype) * 10
+
+
+def test_edge_shapes(tb):
+    """Empty batches, 1x1 and tiny matrices, odd column counts with beta, strided (ld > n) matrices."""
+    rng = np.random.default_rng(22)
+    n = 700
+    Ao, Ad = make_pair(tb, "toeplitz", n, np.float64)
+    F = tb.factorize(Ad)
+    # zero columns: nothing to do, no error
+    Y0 = tb.colmajor(n, 0)
+    assert tb.mul_(Y0, F, tb.colmajor(n, 0)).shape == (n, 0)
+    # odd column count, beta != 0 (pair packing with a dangling column)
+    X = rng.standard_normal((n, 5))
+    Yi = rng.standard_normal((n, 5))
+    Yd = devmat(Yi.copy())
+    tb.mul_(Yd, F, devmat(X), 1.0, 1.0)
+    assert rel(host(Yd), Ao.dense() @ X + Yi) <= TOL64
+    # leading dimension larger than the row count (views into a taller matrix)
+    big_x = torch.zeros((5, n + 37), dtype=torch.float64, device="cuda")
+    big_y = torch.full((5, n + 11), np.nan, dtype=torch.float64, device="cuda")
+    big_x[:, :n] = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+    tb.mul_(big_y.t()[:n, :], F, big_x.t()[:n, :])
+    assert rel(host(big_y[:, :n].t()), Ao.dense() @ X) <= TOL64
+    assert torch.isnan(big_y[:, n:]).all()
+    # 1x1 and 2x3 matrices (vector path: direct; matrix path: FFT with the minimum embedding)
+    T1 = tb.Toeplitz(dev(np.array([2.5])), dev(np.array([2.5])))
+    assert host(tb.mul(T1, dev(np.array([4.0]))))[0] == 10.0
+    T23o = O.Toeplitz(np.array([1.0, 2.0]), np.array([1.0, 3.0, 4.0]))
+    T23 = tb.Toeplitz(dev(T23o.vc), dev(T23o.vr))
+    X3 = rng.standard_normal((3, 4))
+    assert rel(host(tb.mul(T23, devmat(X3))), T23o.dense() @ X3) <= TOL64
+    # Hankel with surplus anti-diagonals: the reference's mul! fails its size check (src/hankel.jl:117)
+    with pytest.raises(tb.DimensionMismatch):
+        tb.mul(tb.Hankel(dev(np.arange(12.0)), (5, 5)), dev(np.ones(5)))
+    # levinson on zero systems
+    assert tb.levinson_(tb.colmajor(8, 0), tb.colmajor(7, 0), tb.colmajor(8, 0)).shape == (8, 0)

@@ -371,6 +371,11 @@ def mul_(y: torch.Tensor, A, x: torch.Tensor, alpha=True, beta=False) -> torch.T
         if y.shape[0] != m or x.shape[0] != n:
             raise DimensionMismatch("Toeplitz factorization does not match size of input and output vector")
     else:
+        if isinstance(A, Hankel) and A.v.shape[0] != A.shape[0] + A.shape[1] - 1:
+            # reverse(A, dims=2) keeps the surplus tail of v (src/hankel.jl:117), so the Toeplitz it builds is
+            # taller than y and the reference's mul! fails its first size check (src/linearalgebra.jl:8-12)
+            raise DimensionMismatch("first dimension of A, %d, does not match length of y, %d"
+                                    % (A.v.shape[0] - A.shape[1] + 1, y.shape[0]))
         _check_mul_dims(y, A.shape, x)
     if not _promote_eltype(y, A, x, alpha, beta) and _is_real(y.dtype):
         raise ArgumentError("InexactError: cannot store a complex product into a real y")

@@ -122,6 +122,9 @@ k_rows(const ConvArgs<R> p) {
     const int slot = threadIdx.x / NT, t = threadIdx.x % NT;
     cx<R>* sm = reinterpret_cast<cx<R>*>(smraw) + slot * L;
     RowMap<R> map;
+#ifdef TB_EXP_SKEW          // experiment: de-phase the two CTAs that share an SM
+    if ((blockIdx.x / 148) & 1) __nanosleep(TB_EXP_SKEW);
+#endif
 
     for (long long f0 = (long long)blockIdx.x * TS; f0 < p.nfft; f0 += (long long)gridDim.x * TS) {
         const long long f = f0 + slot;
