@@ -241,6 +241,16 @@ struct tb200_fact {
 
 namespace tb {
 
+// A handle is bound to the device it was created on; entry points switch to it for the call.
+struct DeviceGuard {
+    int prev = -1; bool switched = false;
+    explicit DeviceGuard(const tb200_fact* h) {
+        if (!h) return;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != h->device) { cudaSetDevice(h->device); switched = true; }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 static int next_log2(int64_t v) { int l = 0; while ((1ll << l) < v) ++l; return l; }
 
 static int make_plan(tb200_fact* h) {
@@ -746,6 +756,7 @@ int tb200_factorize_host(int kind, int dtype, int64_t m, int64_t n, const void* 
 }
 
 int tb200_destroy(tb200_handle_t h) {
+    DeviceGuard dev_guard(h);
     delete h;
     return TB200_OK;
 }
@@ -808,12 +819,14 @@ static int mul_impl(tb200_fact* h, const void* spec, bool is_ldiv, void* y, int6
 
 int tb200_mul(tb200_handle_t h, void* y, int64_t ldy, int ydtype, const void* x, int64_t ldx, int xdtype, int64_t ncols,
               const double alpha[2], const double beta[2], void* stream) {
+    DeviceGuard dev_guard(h);
     if (!h) return set_error(TB200_BAD_ARG, "handle is NULL");
     return mul_impl(h, h->spec->p, false, y, ldy, ydtype, x, ldx, xdtype, ncols, alpha, beta, (cudaStream_t)stream);
 }
 
 int tb200_mul_host(tb200_handle_t h, void* y_host, int64_t ldy, int ydtype, const void* x_host, int64_t ldx, int xdtype,
                    int64_t ncols, const double alpha[2], const double beta[2]) {
+    DeviceGuard dev_guard(h);
     if (!h) return set_error(TB200_BAD_ARG, "handle is NULL");
     if (!dt_valid(xdtype) || !dt_valid(ydtype)) return set_error(TB200_BAD_ARG, "unknown dtype");
     if (ncols <= 0) return TB200_OK;
@@ -943,6 +956,7 @@ static int ensure_inv_spec(tb200_fact* h, cudaStream_t s) {
 
 int tb200_circ_ldiv(tb200_handle_t h, void* x, int64_t ldx, const void* b, int64_t ldb, int dtype, int64_t ncols,
                     void* stream) {
+    DeviceGuard dev_guard(h);
     TB_TRY(require_circulant(h));
     TB_TRY(ensure_inv_spec(h, (cudaStream_t)stream));
     const double one[2] = {1, 0}, zero[2] = {0, 0};
@@ -951,6 +965,7 @@ int tb200_circ_ldiv(tb200_handle_t h, void* x, int64_t ldx, const void* b, int64
 }
 
 int tb200_circ_spectrum(tb200_handle_t h, void* out, void* stream) {
+    DeviceGuard dev_guard(h);
     TB_TRY(require_circulant(h));
     if (!out) return set_error(TB200_BAD_ARG, "out is NULL");
     cudaStream_t s = (cudaStream_t)stream;
@@ -972,6 +987,7 @@ static int clone_plan(tb200_fact* h, tb200_fact** out) {
 }
 
 int tb200_circ_map(tb200_handle_t h, int op, double tol, void* stream, tb200_handle_t* out) {
+    DeviceGuard dev_guard(h);
     TB_TRY(require_circulant(h));
     if (!out) return set_error(TB200_BAD_ARG, "out is NULL");
     if (op < 0 || op > 4) return set_error(TB200_BAD_ARG, "unknown spectrum op %d", op);
@@ -987,6 +1003,7 @@ int tb200_circ_map(tb200_handle_t h, int op, double tol, void* stream, tb200_han
 }
 
 int tb200_circ_mul(tb200_handle_t a, tb200_handle_t b, void* stream, tb200_handle_t* out) {
+    DeviceGuard dev_guard(a);
     TB_TRY(require_circulant(a));
     TB_TRY(require_circulant(b));
     if (!out) return set_error(TB200_BAD_ARG, "out is NULL");
@@ -1010,6 +1027,7 @@ int tb200_circ_mul(tb200_handle_t a, tb200_handle_t b, void* stream, tb200_handl
 }
 
 int tb200_circ_to_vc(tb200_handle_t h, void* vc_out, int out_dtype, void* stream) {
+    DeviceGuard dev_guard(h);
     TB_TRY(require_circulant(h));
     if (!vc_out) return set_error(TB200_BAD_ARG, "vc_out is NULL");
     if (!dt_valid(out_dtype) || dt_prec(out_dtype) != h->prec) return set_error(TB200_BAD_ARG, "output dtype must have the factorization's precision");
@@ -1236,6 +1254,7 @@ extern "C" {
 
 int tb200_cgs(tb200_handle_t A, tb200_handle_t M, void* x, const void* b, int dtype, int64_t n, int max_it, double tol,
               double* err, int* iter, int* flag, void* stream) {
+    DeviceGuard dev_guard(A);
     TB_TRY(check_krylov(A, M, dtype, n, x, b));
     double e = 0; int it = 0, fl = 0, st;
     cudaStream_t s = (cudaStream_t)stream;
@@ -1253,6 +1272,7 @@ int tb200_cgs(tb200_handle_t A, tb200_handle_t M, void* x, const void* b, int dt
 
 int tb200_cg(tb200_handle_t A, tb200_handle_t M, void* x, const void* b, int dtype, int64_t n, int max_it, double tol,
              double* err, int* iter, int* flag, void* stream) {
+    DeviceGuard dev_guard(A);
     TB_TRY(check_krylov(A, M, dtype, n, x, b));
     if (dt_is_cplx(dtype)) return set_error(TB200_BAD_ARG, "cg is defined for real (BlasReal) element types only");
     double e = 0; int it = 0, fl = 0, st;
