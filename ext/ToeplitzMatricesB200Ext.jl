@@ -205,4 +205,31 @@ function ToeplitzMatrices.levinson!(x::Union{DV{T},DM{T}}, r::Union{DV{T},DM{T}}
     x
 end
 
+# ---- trench (src/directLinearSolvers.jl:36-85) and triangular inverse (src/linearalgebra.jl:337-396) ----
+function ToeplitzMatrices.trench(T::SymmetricToeplitz{S,<:DV}) where {S<:Union{Float32,Float64}}
+    n = size(T, 1)
+    r0 = Array(T.vc[1:1])[1]
+    r = isone(r0) ? T.vc[2:end] : T.vc[2:end] ./ r0
+    B = CuMatrix{S}(undef, n, n)
+    check(ccall((:tb200_trench, libtb), Cint, (Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cdouble, Ptr{Cvoid}),
+                dtcode(S), n, devptr(r), devptr(B), n, Float64(r0), curstream()))
+    Symmetric(B)
+end
+function _tri_inv_lower(v::DV{T}) where {T}
+    n = length(v)
+    if n <= 64
+        out = similar(v)
+        check(ccall((:tb200_tri_smallinv, libtb), Cint, (Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                    dtcode(T), n, devptr(v), devptr(out), curstream()))
+        return out
+    end
+    np2 = nextpow(2, n)
+    n != np2 && return _tri_inv_lower([v; fill!(similar(v, np2 - n), 0)])[1:n]
+    nd2 = div(n, 2)
+    a1 = _tri_inv_lower(v[1:nd2])
+    [a1; -(LowerTriangularToeplitz(a1) * (Toeplitz(v[nd2+1:end], v[nd2+1:-1:2]) * a1))]
+end
+inv(A::LowerTriangularToeplitz{T,<:DV}) where {T} = LowerTriangularToeplitz(_tri_inv_lower(A.v))
+inv(A::UpperTriangularToeplitz{T,<:DV}) where {T} = UpperTriangularToeplitz(_tri_inv_lower(A.v))
+
 end # module

@@ -126,6 +126,15 @@ int tb200_levinson_batched(int dtype, int64_t n, int64_t nsys, const void* r, in
 int tb200_durbin_batched(int dtype, int64_t n, int64_t nsys, const void* r, int64_t ldr,
                          void* y, int64_t ldy, void* stream);
 
+/* trench(T::SymmetricToeplitz) src/directLinearSolvers.jl:36-85: B (n x n, column-major, ldb) = inv(T) for the
+ * SPD matrix T = diag * SymToeplitz([1; r]); r has n-1 entries (already divided by diag, :51-53), real dtype.
+ * Durbin + the anti-diagonal recurrence fill; both triangles are written (the reference fills the upper one and
+ * wraps it in Symmetric).                                                                                     */
+int tb200_trench(int dtype, int64_t n, const void* r, void* B, int64_t ldb, double diag, void* stream);
+/* smallinv(::LowerTriangularToeplitz) src/linearalgebra.jl:337-349: out = first column of inv(L(v)), n <= 64.
+ * Base case of the recursive-doubling triangular inverse (:350-396), whose products go through tb200_mul*.    */
+int tb200_tri_smallinv(int dtype, int64_t n, const void* v, void* out, void* stream);
+
 /* ---- iterative solvers ---------------------------------------------------------------
  * IterativeLinearSolvers.cgs src/iterativeLinearSolvers.jl:99-215 and cg :9-97 with A a
  * factorized structured matrix and M a Circulant factorization (factorize(strang(A)) /

@@ -752,3 +752,34 @@ def trench(r_or_T):
         for i in range(2, j + 1):
             B[i - 1, j - 1] = B[i - 2, j - 2] + (nu[n - j] * nu[n - i] - nu[i - 2] * nu[j - 2]) / gamma
     return np.triu(B) + np.triu(B, 1).T
+
+
+# ----------------------------------------------------------------------------
+# triangular inverse by recursive doubling (src/linearalgebra.jl:337-396), SURVEY 8f rank 2
+# ----------------------------------------------------------------------------
+def tri_smallinv_lower(v):
+    """``smallinv(A::LowerTriangularToeplitz)`` :337-349 -> first column of the inverse."""
+    n = len(v)
+    b = np.zeros(n, dtype=v.dtype)
+    b[0] = 1 / v[0]
+    for k in range(1, n):
+        tmp = v.dtype.type(0)
+        for i in range(k):
+            tmp += v[k - i] * b[i]
+        b[k] = -tmp / v[0]
+    return b
+
+
+def tri_inv_lower(v):
+    """``inv(A::LowerTriangularToeplitz)`` :350-365 -> first column of the inverse."""
+    n = len(v)
+    if n <= 64:
+        return tri_smallinv_lower(v)
+    np2 = 1 << (n - 1).bit_length()
+    if n != np2:
+        return tri_inv_lower(np.concatenate([v, np.zeros(np2 - n, dtype=v.dtype)]))[:n]
+    nd2 = n // 2
+    a1 = tri_inv_lower(v[:nd2])
+    T = Toeplitz(v[nd2:], v[nd2:0:-1])
+    t = matvec(T, a1)
+    return np.concatenate([a1, -matvec(LowerTriangularToeplitz(a1), t)])

@@ -434,3 +434,35 @@ def test_edge_shapes(tb):
         tb.mul(tb.Hankel(dev(np.arange(12.0)), (5, 5)), dev(np.ones(5)))
     # levinson on zero systems
     assert tb.levinson_(tb.colmajor(8, 0), tb.colmajor(7, 0), tb.colmajor(8, 0)).shape == (8, 0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 8, 64, 65, 128, 700, 3000])
+def test_triangular_inverse(tb, n):
+    """inv(::Lower/UpperTriangularToeplitz) by recursive doubling (src/linearalgebra.jl:337-396), SURVEY 8f-2."""
+    for dtype in (np.float64, np.complex128):
+        v = np.concatenate([[1.0], 0.5 * 0.7 ** np.arange(1, n)]).astype(dtype)
+        if np.dtype(dtype).kind == "c":
+            v = v * np.exp(0.3j * np.arange(n))
+        ref = O.tri_inv_lower(v)
+        assert rel(host(tb.inv(tb.LowerTriangularToeplitz(dev(v))).v), ref) <= 1e-11
+        Ui = tb.inv(tb.UpperTriangularToeplitz(dev(v)))
+        assert isinstance(Ui, tb.UpperTriangularToeplitz)
+        if n <= 700:
+            dense = np.linalg.inv(O.UpperTriangularToeplitz(v).dense())
+            assert rel(O.UpperTriangularToeplitz(host(Ui.v)).dense(), dense) <= 1e-10
+
+
+@pytest.mark.parametrize("n", [1, 2, 9, 100, 513, 1500])
+def test_trench(tb, n):
+    """trench(T) (src/directLinearSolvers.jl:36-85; test/runtests.jl:129-135), SURVEY 8f-3."""
+    rng = np.random.default_rng(n)
+    a = np.concatenate([[1.0], rng.random(n - 1) / max(n, 2)])
+    T = O.SymmetricToeplitz(a)
+    B = host(tb.trench(tb.SymmetricToeplitz(dev(a))))
+    assert rel(B, np.linalg.inv(T.dense())) <= 1e-10
+    if 2 <= n <= 100:
+        assert rel(B, O.trench(T)) <= 1e-12
+    TS = O.SymmetricToeplitz(2.3 * a)
+    assert rel(host(tb.trench(tb.SymmetricToeplitz(dev(2.3 * a)))), np.linalg.inv(TS.dense())) <= 1e-10
+    if n >= 2:
+        assert rel(host(tb.trench(dev(a[1:].copy()))), np.linalg.inv(T.dense())) <= 1e-10

@@ -256,3 +256,13 @@ def test_cgs_flags_and_pad_invariance():
     xp[:700] = xx
     yp = np.fft.ifft(np.fft.fft(xp) * np.fft.fft(c)).real[:700]
     assert approx(yp, O.matvec(T, xx), 1e-13)
+
+
+def test_triangular_inverse_recursive_doubling():
+    """src/linearalgebra.jl:337-365 restated; test/runtests.jl:637-639,656-662 (lower branch) vs the dense inverse
+    on a well-conditioned decaying column."""
+    for n in (2, 64, 65, 128, 200):
+        v = np.concatenate([[1.0], 0.5 * 0.7 ** np.arange(1, n)])
+        Linv = O.tri_inv_lower(v)
+        dense = np.linalg.inv(O.LowerTriangularToeplitz(v).dense())
+        assert approx(O.LowerTriangularToeplitz(Linv).dense(), dense, 1e-10)

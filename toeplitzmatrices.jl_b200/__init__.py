@@ -9,6 +9,6 @@ from ._lib import (ArgumentError, DimensionMismatch, ToeplitzB200Error, EXPORTS,
 from .api import *  # noqa: F401,F403
 from .api import (Toeplitz, SymmetricToeplitz, Circulant, LowerTriangularToeplitz, UpperTriangularToeplitz,  # noqa: F401
                   Hankel, ToeplitzFactorization, factorize, mul_, mul, ldiv_, ldiv, circ_ldiv_, eigvals, det, inv,
-                  pinv, sqrt, circ_mul, adjoint, transpose, strang, chan, durbin, durbin_, levinson, levinson_,
+                  pinv, sqrt, circ_mul, adjoint, transpose, strang, chan, durbin, durbin_, levinson, levinson_, trench,
                   cgs, cg, colmajor, to_colmajor, mul_host_, factorize_host, spectrum_tensor,
                   factorize_empty_like, launch_count, set_option, pass_times)

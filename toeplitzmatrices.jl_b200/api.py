@@ -540,8 +540,35 @@ def det(C):
     return d.real if _is_real(C.dtype) else d
 
 
+def _tri_inv_lower(v: torch.Tensor) -> torch.Tensor:
+    """First column of ``inv(LowerTriangularToeplitz(v))`` by recursive doubling (:337-365); every product
+    is a device ``mul`` (direct kernel below N = 512, FFT above), the n <= 64 base case one small kernel."""
+    n = v.shape[0]
+    if n <= 64:
+        out = torch.empty_like(v)
+        check(L.lib().tb200_tri_smallinv(_DT[v.dtype], n, v.data_ptr(), out.data_ptr(), _stream()))
+        return out
+    np2 = 1 << (n - 1).bit_length()
+    if n != np2:
+        vp = torch.zeros(np2, dtype=v.dtype, device=v.device)
+        vp[:n] = v
+        return _tri_inv_lower(vp)[:n].contiguous()
+    nd2 = n // 2
+    a1 = _tri_inv_lower(v[:nd2].contiguous())
+    T = Toeplitz(v[nd2:].contiguous(), v[1:nd2 + 1].flip(0).contiguous())
+    t = mul(T, a1)
+    return torch.cat([a1, -mul(LowerTriangularToeplitz(a1), t)])
+
+
 def inv(C):
-    """``inv(C::Circulant)`` -> Circulant (:244-249); ``inv(F)`` -> factorization (:250-253)."""
+    """``inv(C::Circulant)`` -> Circulant (:244-249); ``inv(F)`` -> factorization (:250-253);
+    ``inv(::Lower/UpperTriangularToeplitz)`` -> triangular Toeplitz (:337-396).  The upper inverse uses the
+    coefficients of the lower one (inv(U(v)) = U(inv(L(v)).v)); the reference's own upper branch is
+    ``@test_broken`` (test/runtests.jl:660), so it is matched against the dense inverse instead."""
+    if isinstance(C, LowerTriangularToeplitz):
+        return LowerTriangularToeplitz(_tri_inv_lower(C.v))
+    if isinstance(C, UpperTriangularToeplitz):
+        return UpperTriangularToeplitz(_tri_inv_lower(C.v))
     if isinstance(C, ToeplitzFactorization):
         return _circ_map(_circ_fact(C), L.OP_INV)
     return _to_circulant(_circ_map(_circ_fact(C), L.OP_INV), C.dtype)
@@ -654,6 +681,24 @@ def levinson(r_or_T, b: torch.Tensor) -> torch.Tensor:
         return levinson_(x, r, b, diag)
     r = to_colmajor(_floatify(r_or_T).to(b.dtype))
     return levinson_(x, r, b)
+
+
+def trench(r_or_T) -> torch.Tensor:
+    """``trench(T::SymmetricToeplitz)`` / ``trench(r)`` (:36-85): dense inverse of the SPD matrix, O(n^2)
+    (Durbin + the anti-diagonal recurrence).  Returns the full symmetric ``n x n`` matrix (column-major)."""
+    if isinstance(r_or_T, SymmetricToeplitz):
+        vc = r_or_T.vc
+        r0 = float(vc[0].item())
+        r = (vc[1:] / r0).contiguous() if r0 != 1.0 else vc[1:].contiguous()
+    else:
+        r = _floatify(r_or_T).contiguous()
+        r0 = 1.0
+    if not _is_real(r.dtype):
+        raise ArgumentError("trench needs a real symmetric positive definite Toeplitz matrix")
+    n = r.shape[0] + 1
+    B = colmajor(n, n, r.dtype, r.device)
+    check(L.lib().tb200_trench(_DT[r.dtype], n, r.data_ptr() if n > 1 else None, B.data_ptr(), _ld(B), r0, _stream()))
+    return B
 
 
 # ------------------------------------------------------------------------------------

@@ -192,6 +192,56 @@ __global__ void k_bs_post(void* y, long long ldy, int y_cplx, const cx<R>* __res
     }
 }
 
+// smallinv(::LowerTriangularToeplitz) (src/linearalgebra.jl:337-349): first column b of inv(L(v)) by forward
+// substitution, n <= 64 (the base case of the recursive-doubling inverse).  One thread: the recurrence is
+// sequential and tiny.  Same accumulation order as the reference.
+template <typename R>
+__global__ void k_tri_smallinv(void* bout, const void* v, int cplx, int n) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    cx<R> b[64];
+    const cx<R> v0 = load_a<R>(v, cplx, 0);
+    const R den = v0.x * v0.x + v0.y * v0.y;
+    const cx<R> iv0 = cplx ? mk<R>(v0.x / den, -v0.y / den) : mk<R>((R)1 / v0.x, 0);
+    b[0] = iv0;
+    for (int k = 1; k < n; ++k) {
+        cx<R> tmp = mk<R>(0, 0);
+        for (int i = 0; i < k; ++i) {
+            const cx<R> pr = cmul(load_a<R>(v, cplx, k - i), b[i]);
+            tmp.x += pr.x; tmp.y += pr.y;
+        }
+        const cx<R> q = cplx ? cmul(tmp, iv0) : mk<R>(tmp.x / v0.x, 0);
+        b[k] = mk<R>(-q.x, -q.y);
+    }
+    for (int k = 0; k < n; ++k) {
+        if (cplx) reinterpret_cast<cx<R>*>(bout)[k] = b[k];
+        else reinterpret_cast<R*>(bout)[k] = b[k].x;
+    }
+}
+
+// trench!(B, r) fill (src/directLinearSolvers.jl:71-85): with y = durbin(r), gamma = 1/(1 + r.y),
+// nu = gamma*reverse(y):  B[1,1] = gamma, B[1,2:n] = gamma*y,
+// B[i,j] = B[i-1,j-1] + (nu[n+1-j] nu[n+1-i] - nu[i-1] nu[j-1]) / gamma  (2 <= i <= j).
+// One thread per diagonal d = j - i walks down its diagonal (the recurrence is sequential along it);
+// both triangles are written so the result is the full symmetric inverse; scaled by 1/diag.
+template <typename R>
+__global__ void k_trench_fill(R* __restrict__ B, long long ldb, const R* __restrict__ y, const double* __restrict__ dots,
+                              long long n, R inv_diag) {
+    const long long d = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    const R gamma = (R)(1.0 / (1.0 + dots[0]));
+    // nu[k] (1-based, k = 1..n-1) = gamma * y[n-k] (1-based y) = gamma * y0[n-1-k] (0-based)
+    auto nu = [&](long long k) { return gamma * y[n - 1 - k]; };
+    R b = (d == 0) ? gamma : gamma * y[d - 1];                         // B[1, 1+d]
+    B[0 + d * ldb] = b * inv_diag;
+    B[d + 0 * ldb] = b * inv_diag;
+    for (long long i = 2; i + d <= n; ++i) {                            // 1-based i, j = i + d
+        const long long j = i + d;
+        b += (nu(n + 1 - j) * nu(n + 1 - i) - nu(i - 1) * nu(j - 1)) / gamma;
+        B[(i - 1) + (j - 1) * ldb] = b * inv_diag;
+        B[(j - 1) + (i - 1) * ldb] = b * inv_diag;
+    }
+}
+
 // strang / chan (src/linearalgebra.jl:255-274), elementwise on device.
 template <typename R>
 __global__ void k_strang_chan(void* vout, int which, int kind, const void* vc, const void* vr, int a_cplx, long long n) {

@@ -1073,6 +1073,47 @@ int tb200_durbin_batched(int dtype, int64_t n, int64_t nsys, const void* r, int6
     return levinson_dispatch(dtype, true, n, nsys, r, ldr, nullptr, 0, y, ldy, nullptr, (cudaStream_t)stream);
 }
 
+int tb200_tri_smallinv(int dtype, int64_t n, const void* v, void* out, void* stream) {
+    if (!dt_valid(dtype)) return set_error(TB200_BAD_ARG, "unknown dtype");
+    if (n < 1 || n > 64) return set_error(TB200_BAD_ARG, "smallinv is the n <= 64 base case, got n = %lld", (long long)n);
+    if (!v || !out) return set_error(TB200_BAD_ARG, "NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dt_prec(dtype)) k_tri_smallinv<double><<<1, 32, 0, s>>>(out, v, dt_is_cplx(dtype), (int)n);
+    else k_tri_smallinv<float><<<1, 32, 0, s>>>(out, v, dt_is_cplx(dtype), (int)n);
+    count_launch();
+    return cuda_status(cudaGetLastError(), "k_tri_smallinv");
+}
+
+int tb200_trench(int dtype, int64_t n, const void* r, void* B, int64_t ldb, double diag, void* stream) {
+    if (dtype != TB200_F32 && dtype != TB200_F64) return set_error(TB200_UNSUPPORTED, "trench: real Float32/Float64 only");
+    if (n < 1) return set_error(TB200_BAD_ARG, "bad size");
+    if (!B || (n > 1 && !r)) return set_error(TB200_BAD_ARG, "NULL argument");
+    if (ldb < n) return set_error(TB200_DIM_MISMATCH, "B must be %lld x %lld", (long long)n, (long long)n);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t esz = dt_prec(dtype) ? 8 : 4;
+    std::shared_ptr<DevBuf> ybuf, scal;
+    TB_TRY(dev_alloc(ybuf, esz * (size_t)std::max<int64_t>(n - 1, 1), "trench durbin vector"));
+    TB_TRY(dev_alloc(scal, sizeof(double) * 4 * 64 + 64, "trench scalars"));
+    double* dots = (double*)scal->p;
+    double* partials = dots + 4;
+    unsigned* counter = (unsigned*)(partials + 4 * 60);
+    TB_CUDA(cudaMemsetAsync(scal->p, 0, scal->bytes, s), "memset");
+    if (n > 1) {
+        TB_TRY(levinson_dispatch(dtype, true, n - 1, 1, r, n - 1, nullptr, 0, ybuf->p, n - 1, nullptr, s));   // y = durbin(r)
+        const unsigned grid = std::min<unsigned>(ew_grid(n - 1), 60u);
+        if (dt_prec(dtype)) k_dot2<double><<<grid, 256, 0, s>>>((const double*)r, (const double*)ybuf->p, nullptr, nullptr, n - 1, partials, counter, dots);
+        else k_dot2<float><<<grid, 256, 0, s>>>((const float*)r, (const float*)ybuf->p, nullptr, nullptr, n - 1, partials, counter, dots);
+        count_launch();
+    }
+    const unsigned g2 = (unsigned)((n + 127) / 128);
+    if (dt_prec(dtype)) k_trench_fill<double><<<g2, 128, 0, s>>>((double*)B, ldb, (const double*)ybuf->p, dots, n, 1.0 / diag);
+    else k_trench_fill<float><<<g2, 128, 0, s>>>((float*)B, ldb, (const float*)ybuf->p, dots, n, (float)(1.0 / diag));
+    count_launch();
+    TB_CUDA(cudaGetLastError(), "trench kernels");
+    TB_CUDA(cudaStreamSynchronize(s), "trench sync");       // temporaries are released on return
+    return TB200_OK;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------
