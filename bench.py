@@ -261,6 +261,8 @@ def run_ours(args):
 
     # ---- end-to-end through the host-buffer C-ABI call (pinned host in, pinned host out)
     e2e_steps = max(1, min(args.steps, 3))
+    # host staging is pinned memory: bound it per rank when several ranks share one host (8 x 16 GiB would not be polite)
+    e2e_cols = ncols if world == 1 else min(ncols, 512)
     if args.no_e2e:
         if world > 1:
             dist.destroy_process_group()
@@ -268,9 +270,9 @@ def run_ours(args):
             print(json.dumps({"value": value, "ms_per_step": ms / args.steps, "pass_ms": pass_ms, "pass_cnt": pass_cnt,
                               "launches": launches, "clocks": clocks}), flush=True)
         return
-    Xh = torch.empty((ncols, n), dtype=torch.float64).pin_memory().t()
-    Yh = torch.empty((ncols, n), dtype=torch.float64).pin_memory().t()
-    Xh.copy_(X)
+    Xh = torch.empty((e2e_cols, n), dtype=torch.float64).pin_memory().t()
+    Yh = torch.empty((e2e_cols, n), dtype=torch.float64).pin_memory().t()
+    Xh.copy_(X[:, :e2e_cols])
     torch.cuda.synchronize()
     tb.mul_host_(Yh, F, Xh)             # warm-up (allocates staging buffers, touches pages)
     if world > 1:
@@ -284,7 +286,7 @@ def run_ours(args):
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_val = world * ncols * e2e_steps / e2e_s
+    e2e_val = world * e2e_cols * e2e_steps / e2e_s
     e2e_err = float((Yh[:, :2] - Y[:, :2].cpu()).abs().max())
 
     if rank != 0:
@@ -334,8 +336,8 @@ def run_ours(args):
         "config": {"workload": "Toeplitz{Float64} n=2^20 x Matrix with %d RHS columns per GPU (BASELINE configs[1])" % ncols,
                    "n": n, "columns_per_gpu": ncols, "parallelism": "columns sharded over %d GPU(s), spectrum broadcast once" % world,
                    "l2": "inputs (8 GiB X + 8 GiB Y per GPU) far exceed the 126 MB L2; no flush needed"},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": ncols * n * 8, "d2h_bytes_per_step": ncols * n * 8,
-                "steps": e2e_steps, "max_abs_diff_vs_device_path": e2e_err},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": e2e_cols * n * 8, "d2h_bytes_per_step": e2e_cols * n * 8,
+                "steps": e2e_steps, "columns_per_gpu_per_step": e2e_cols, "max_abs_diff_vs_device_path": e2e_err},
         "gpu_launches": int(launches),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity_rel_err_vs_oracle": parity,
     }
