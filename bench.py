@@ -299,7 +299,7 @@ def run_ours(args):
     dom = max(pass_ms, key=lambda k: pass_ms[k])
     per_launch_ms = pass_ms[dom] / max(pass_cnt[dom], 1)
     cols_per_launch = ncols * args.steps / max(pass_cnt[dom], 1)
-    achieved = ALG_BYTES_PER_MATVEC * cols_per_launch / (per_launch_ms * 1e-3) / 1e9
+    achieved = (ALG_BYTES_PER_MATVEC * cols_per_launch / (per_launch_ms * 1e-3) / 1e9) if per_launch_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):

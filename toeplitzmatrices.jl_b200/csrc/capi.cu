@@ -33,7 +33,7 @@ static std::atomic<int> g_time_passes{0};
 static std::atomic<int> g_overlap_streams{2};   // helper streams for group overlap (0/1 = off)
 static std::atomic<int> g_mega{0};               // opt-in persistent single-launch path (measured slower than 3 kernels x 2 streams)
 static std::atomic<int> g_pipe_b{0};             // opt-in cp.async double-buffered persistent pass B (measured slower)
-static std::atomic<int> g_l2max_f64{12}, g_l2max_f32{13}, g_ta_cap{0};   // plan tuning knobs
+static std::atomic<int> g_l2max_f64{12}, g_l2max_f32{13}, g_ta_cap{0}, g_force_l1{0};   // plan tuning knobs
 
 // optional per-pass device timing (bench.py's roofline leg): CUDA events recorded on the
 // launching stream around every pass while "time_passes" is on.
@@ -271,6 +271,7 @@ static int make_plan(tb200_fact* h) {
         return set_error(TB200_UNSUPPORTED, "embedding length 2^%d exceeds the two-level plan (max 2^%d)", l,
                          l1max + (h->prec ? 13 : 14));
     if (l1 < 6) { l1 = 6; l2 = l - l1; }
+    if (g_force_l1.load() >= 6 && l - g_force_l1.load() >= 4 && l - g_force_l1.load() <= (h->prec ? 13 : 14)) { l1 = g_force_l1.load(); l2 = l - l1; }
     const int full = 128 / (int)(h->prec ? 16 : 8);            // columns per 128-byte line
     int ta = full;
     const size_t esz = h->prec ? 16 : 8;
@@ -703,6 +704,7 @@ int tb200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "l2max_f64")) { g_l2max_f64 = (int)value; return TB200_OK; }
     if (!strcmp(name, "l2max_f32")) { g_l2max_f32 = (int)value; return TB200_OK; }
     if (!strcmp(name, "ta_cap")) { g_ta_cap = (int)value; return TB200_OK; }
+    if (!strcmp(name, "force_l1")) { g_force_l1 = (int)value; return TB200_OK; }
     if (!strcmp(name, "mega")) { g_mega = value ? 1 : 0; return TB200_OK; }
     if (!strcmp(name, "pipe_b")) { g_pipe_b = value ? 1 : 0; return TB200_OK; }
     return set_error(TB200_BAD_ARG, "unknown option '%s'", name);

@@ -106,6 +106,9 @@ struct OutView {
 // occupancy target: 128 registers/thread for Float64, 64 for Float32, limited by shared memory
 template <typename R>
 constexpr int min_ctas(int threads, int smem_bytes) {
+#ifdef TB_EXP_MINCTAS
+    if (sizeof(R) == 8 && threads == 256) return TB_EXP_MINCTAS;
+#endif
     int by_regs = 65536 / (threads * 2 * ((sizeof(R) == 8 ? 4 : 2) << le_of<R>()));   // budget: 2x the data registers
     int by_smem = (220 * 1024) / (smem_bytes > 0 ? smem_bytes : 1);
     int m = by_regs < by_smem ? by_regs : by_smem;
