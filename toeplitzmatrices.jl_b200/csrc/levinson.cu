@@ -41,21 +41,37 @@ __device__ __forceinline__ void warp_sum2(R& d1, R& d2, int lane) {
     d2 = __shfl_sync(0xffffffffu, keep, 16);
 }
 
-__device__ __forceinline__ double fast_rcp(double x) { return 1.0 / x; }
+// 1/x without the IEEE slow path: hardware seed (MUFU.RCP64H) + three Newton steps (error <~ 1 ulp; beta is a
+// product of (1 - alpha^2) factors of an SPD recursion, i.e. finite, positive and far from the denormal range).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
 __device__ __forceinline__ float fast_rcp(float x) { return 1.0f / x; }
 
-// shift the first SROWS super-rows of v up by one element, inserting `head` at index 0
-template <typename R, int SROWS>
+// Shifting vectors (yh, rh) are never moved between registers: a compile-time phase ph (= number of shifts so far
+// mod 4) maps the logical slot q of a lane's block of four to the physical register (q - ph) mod 4, so growing the
+// order by one is ONE in-place rotate-shuffle per super-row (the register that held slot 3 becomes slot 0 of the next
+// lane) plus a phase increment -- no register copies.  Stationary vectors (x, y) use physical == logical.
+__device__ __forceinline__ constexpr int phys(int i, int ph) { return (i & ~(LB - 1)) | (((i & (LB - 1)) - ph) & (LB - 1)); }
+
+// shift the first SROWS super-rows of v (currently at phase PH) up by one element, inserting `head` at logical index 0;
+// afterwards the vector is at phase (PH + 1) mod 4
+template <typename R, int SROWS, int PH>
 __device__ __forceinline__ void shift_up(R* v, R head, int lane) {
     R carry = head;                // value entering lane 0 of the current super-row
 #pragma unroll
     for (int s = 0; s < SROWS; ++s) {
-        const R rot = __shfl_sync(0xffffffffu, v[s * LB + LB - 1], (lane + 31) & 31);
-        const R in0 = (lane == 0) ? carry : rot;
+        constexpr int wrap = (LB - 1 - PH) & (LB - 1);       // physical register holding logical slot 3
+        const R rot = __shfl_sync(0xffffffffu, v[s * LB + wrap], (lane + 31) & 31);
+        v[s * LB + wrap] = (lane == 0) ? carry : rot;
         carry = rot;               // lane 0 sees lane 31's last element: head of the next super-row
-#pragma unroll
-        for (int j = LB - 1; j >= 1; --j) v[s * LB + j] = v[s * LB + j - 1];
-        v[s * LB] = in0;
     }
 }
 
@@ -65,47 +81,67 @@ struct LevState {
     R alpha, beta;
 };
 
+// one recursion step k = SC*128 + lb*4 + J at compile-time block position J (phase of yh/rh before the step: (J+3)%4)
+template <typename R, int S, int SC, int J, bool DURBIN, bool INTERIOR = false>
+__device__ __forceinline__ void lev_step(LevState<R, S>& st, int k, int n, int lane, int lb, const R* r_s, const R* b_s) {
+    constexpr int ACT = (SC + 1) * LB;
+    constexpr int PH = (J + LB - 1) & (LB - 1);
+    st.beta *= ((R)1 - st.alpha * st.alpha);
+    // one reciprocal per step instead of the reference's two divisions by beta (<= 1 ulp apart);
+    // it depends only on the previous step, so it overlaps the dot products and the reduction
+    const R ibeta = fast_rcp(st.beta);
+    // four partial sums per dot product keep the FMA chains short
+    R p1[LB], p2[LB];
+#pragma unroll
+    for (int q = 0; q < LB; ++q) { p1[q] = 0; p2[q] = 0; }
+#pragma unroll
+    for (int i = 0; i < ACT; ++i) {
+        if (!DURBIN) p1[i % LB] = fma(st.rh[phys(i, PH)], st.x[i], p1[i % LB]);
+        p2[i % LB] = fma(st.rh[phys(i, PH)], st.y[i], p2[i % LB]);
+    }
+    R d1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
+    R d2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
+    if (!DURBIN) warp_sum2(d1, d2, lane);
+    else d2 = warp_sum(d2);
+    if (!DURBIN) {
+        const R mu = (b_s[k] - d1) * ibeta;
+#pragma unroll
+        for (int i = 0; i < ACT; ++i) st.x[i] = fma(mu, st.yh[phys(i, PH)], st.x[i]);
+        if (lane == lb) st.x[SC * LB + J] = mu;
+    }
+    if (DURBIN || INTERIOR || k < n - 1) {
+        const R rk = r_s[k];
+        st.alpha = -(rk + d2) * ibeta;
+#pragma unroll
+        for (int i = 0; i < ACT; ++i) {
+            const R yo = st.y[i];
+            st.y[i] = fma(st.alpha, st.yh[phys(i, PH)], yo);
+            st.yh[phys(i, PH)] = fma(st.alpha, yo, st.yh[phys(i, PH)]);
+        }
+        if (lane == lb) st.y[SC * LB + J] = st.alpha;
+        shift_up<R, SC + 1, PH>(st.yh, st.alpha, lane);
+        shift_up<R, SC + 1, PH>(st.rh, rk, lane);
+    }
+}
+
 // all steps k in super-row SC (k = SC*128 .. SC*128+127), then recurse to SC+1
 template <typename R, int S, int SC, bool DURBIN>
 __device__ __forceinline__ void run_superrows(LevState<R, S>& st, int n, int lane, const R* r_s, const R* b_s) {
     if constexpr (SC < S) {
-        constexpr int ACT = (SC + 1) * LB;
         for (int lb = 0; lb < 32; ++lb) {
-#pragma unroll
-            for (int j = 0; j < LB; ++j) {
-                const int k = SC * LSPAN + lb * LB + j;
-                if (k == 0 || k >= n) continue;
-                st.beta *= ((R)1 - st.alpha * st.alpha);
-                R d1 = 0, d2 = 0;
-#pragma unroll
-                for (int i = 0; i < ACT; ++i) {
-                    if (!DURBIN) d1 = fma(st.rh[i], st.x[i], d1);
-                    d2 = fma(st.rh[i], st.y[i], d2);
-                }
-                if (!DURBIN) warp_sum2(d1, d2, lane);
-                else d2 = warp_sum(d2);
-                // one reciprocal per step instead of the reference's two divisions by beta (<= 1 ulp apart)
-                const R ibeta = fast_rcp(st.beta);
-                if (!DURBIN) {
-                    const R mu = (b_s[k] - d1) * ibeta;
-#pragma unroll
-                    for (int i = 0; i < ACT; ++i) st.x[i] = fma(mu, st.yh[i], st.x[i]);
-                    if (lane == lb) st.x[SC * LB + j] = mu;
-                }
-                if (DURBIN || k < n - 1) {
-                    const R rk = r_s[k];
-                    st.alpha = -(rk + d2) * ibeta;
-#pragma unroll
-                    for (int i = 0; i < ACT; ++i) {
-                        const R yo = st.y[i];
-                        st.y[i] = fma(st.alpha, st.yh[i], yo);
-                        st.yh[i] = fma(st.alpha, yo, st.yh[i]);
-                    }
-                    if (lane == lb) st.y[SC * LB + j] = st.alpha;
-                    shift_up<R, SC + 1>(st.yh, st.alpha, lane);
-                    shift_up<R, SC + 1>(st.rh, rk, lane);
-                }
+            const int k0 = SC * LSPAN + lb * LB;
+            if (k0 >= n) break;
+            if (k0 >= 1 && k0 + LB < n) {      // interior block: four unconditional steps (no control-flow merges,
+                lev_step<R, S, SC, 0, DURBIN, true>(st, k0 + 0, n, lane, lb, r_s, b_s);   // so no register copies)
+                lev_step<R, S, SC, 1, DURBIN, true>(st, k0 + 1, n, lane, lb, r_s, b_s);
+                lev_step<R, S, SC, 2, DURBIN, true>(st, k0 + 2, n, lane, lb, r_s, b_s);
+                lev_step<R, S, SC, 3, DURBIN, true>(st, k0 + 3, n, lane, lb, r_s, b_s);
+                continue;
             }
+            if (k0 + 0 >= 1 && k0 + 0 < n) lev_step<R, S, SC, 0, DURBIN>(st, k0 + 0, n, lane, lb, r_s, b_s);
+            if (k0 + 1 < n) lev_step<R, S, SC, 1, DURBIN>(st, k0 + 1, n, lane, lb, r_s, b_s);
+            if (k0 + 2 < n) lev_step<R, S, SC, 2, DURBIN>(st, k0 + 2, n, lane, lb, r_s, b_s);
+            if (k0 + 3 < n) lev_step<R, S, SC, 3, DURBIN>(st, k0 + 3, n, lane, lb, r_s, b_s);
         }
         run_superrows<R, S, SC + 1, DURBIN>(st, n, lane, r_s, b_s);
     }
