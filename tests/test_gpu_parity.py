@@ -466,3 +466,18 @@ def test_trench(tb, n):
     assert rel(host(tb.trench(tb.SymmetricToeplitz(dev(2.3 * a)))), np.linalg.inv(TS.dense())) <= 1e-10
     if n >= 2:
         assert rel(host(tb.trench(dev(a[1:].copy()))), np.linalg.inv(T.dense())) <= 1e-10
+
+
+def test_mul_host_pageable_and_complex(tb):
+    """tb200_mul_host with pageable (unpinned) host memory, complex data, alpha/beta and a Hankel handle."""
+    n, l = 9000, 7
+    rng = np.random.default_rng(31)
+    v = (rng.standard_normal(2 * n - 1) + 1j * rng.standard_normal(2 * n - 1)).astype(np.complex128)
+    X = (rng.standard_normal((n, l)) + 1j * rng.standard_normal((n, l))).astype(np.complex128)
+    Y0 = (rng.standard_normal((n, l)) + 1j * rng.standard_normal((n, l))).astype(np.complex128)
+    Xh = torch.from_numpy(np.ascontiguousarray(X.T)).t()            # pageable, column-major
+    Yh = torch.from_numpy(np.ascontiguousarray(Y0.T)).t()
+    F = tb.factorize_host(tb.Hankel, torch.from_numpy(v), size=(n, n))
+    tb.mul_host_(Yh, F, Xh, 0.5 - 1j, 2.0)
+    ref = (0.5 - 1j) * O.matvec(O.Hankel(v, (n, n)), X) + 2.0 * Y0
+    assert rel(Yh.numpy(), ref) <= TOL64
