@@ -695,6 +695,11 @@ int tb200_pass_times(double ms[4], int64_t counts[4]) {
     return TB200_OK;
 }
 
+#ifdef TB_EXP_TRACE
+} namespace tb { cudaError_t debug_set_trace(long long* p); } extern "C" {
+int tb200_debug_set_trace(void* p) { return cuda_status(tb::debug_set_trace((long long*)p), "trace"); }
+#endif
+
 int tb200_set_option(const char* name, int64_t value) {
     if (!name) return set_error(TB200_BAD_ARG, "option name is NULL");
     if (!strcmp(name, "group_bytes")) { g_group_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
