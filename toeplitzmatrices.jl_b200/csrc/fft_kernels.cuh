@@ -157,6 +157,12 @@ k_rows(const ConvArgs<R> p) {
         cx<R> a[E];
         TB_TRACE(0);
         const cx<R>* srow = p.spec ? p.spec + (fc % p.spec_rows) * (long long)L + t : nullptr;
+#ifdef TB_EXP_PREFETCH_SPEC     // experiment: pull the spectrum row into L1 while the row itself is in flight
+        if (srow) {
+#pragma unroll
+            for (int i = 0; i < E; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(srow + i * NT));
+        }
+#endif
         if (p.x_mode == IO_SPEC) {
             const cx<R>* xin = reinterpret_cast<const cx<R>*>(p.x) + fc * (long long)L + t;
 #pragma unroll
