@@ -20,11 +20,13 @@ cudaError_t launch_rows_one(const ConvArgs<R>& a, int num_sms, cudaStream_t s) {
     constexpr int threads = (1 << (LOG2L - le_of<R>())) * TS;
     constexpr size_t smem = sizeof(cx<R>) * (size_t)(1 << LOG2L) * TS;
     auto kern = k_rows<R, LOG2L, TS>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};          // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev & 63] = true;
     }
     long long ctas = (a.nfft + TS - 1) / TS;
     long long cap = (long long)num_sms * 16;
@@ -39,11 +41,13 @@ cudaError_t launch_cols_one(const ConvArgs<R>& a, cudaStream_t s) {
     constexpr int threads = (1 << (LOG2L1 - le_of<R>())) * TA;
     constexpr size_t smem = sizeof(cx<R>) * (size_t)(1 << LOG2L1) * TA;
     auto kern = LAST ? k_colsC<R, LOG2L1, TA> : k_colsA<R, LOG2L1, TA>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};          // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev & 63] = true;
     }
     const long long tiles = (1LL << a.log2n2) / TA;
     const long long grid = tiles * a.nfft;

@@ -177,7 +177,10 @@ cudaError_t launch_mega_one(const MegaArgs<R>& a, int num_sms, cudaStream_t s) {
     constexpr size_t smem = sizeof(cx<R>) * (size_t)(1 << LOG2L2);
     static_assert(sizeof(cx<R>) * (size_t)(1 << LOG2L1) * TA <= smem, "column tile must fit the row buffer");
     auto kern = k_mega<R, LOG2L1, LOG2L2, TA>;
-    static int occ = 0;
+    static int occ_of[64] = {};               // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& occ = occ_of[dev & 63];
     if (!occ) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -84,11 +84,13 @@ cudaError_t launch_rowsB_pipe_one(cx<R>* scratch, long long nrows, const cx<R>* 
     constexpr int threads = 1 << (LOG2L - le_of<R>());
     constexpr size_t smem = 3 * sizeof(cx<R>) * (size_t)(1 << LOG2L);
     auto kern = k_rowsB_pipe<R, LOG2L>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};          // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev & 63] = true;
     }
     long long grid = nrows < num_sms ? nrows : num_sms;
     kern<<<(unsigned)grid, threads, smem, s>>>(scratch, nrows, spec, spec_rows, tw);
