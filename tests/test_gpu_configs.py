@@ -136,3 +136,20 @@ def test_c5b_cgs_strang_c32(tb):
             xo, eo, ito, fo = O.cgs(Ao, np.zeros(n, np.complex64), b.copy(), O.factorize(O.strang(Ao)), 4, 0.0)
             assert (ito, fo) == (it, flag)
             assert rel(x.cpu().numpy(), xo) <= 1e-4
+
+
+def test_largest_float64_embedding(tb):
+    """Float64 n = 2^24 (embedding 2^25 = 2^12 x 2^13, the largest Float64 two-level plan): one vector vs the oracle."""
+    n = 1 << 24
+    rng = np.random.default_rng(9)
+    vc = rng.standard_normal(n)
+    vr = rng.standard_normal(n)
+    vr[0] = vc[0]
+    x = rng.standard_normal(n)
+    y = tb.mul(tb.Toeplitz(torch.from_numpy(vc).cuda(), torch.from_numpy(vr).cuda()), torch.from_numpy(x).cuda())
+    yo = O.matvec(O.Toeplitz(vc, vr), x, workers=-1)
+    assert rel(y.cpu().numpy(), yo) <= 1e-12
+    with pytest.raises(tb.ToeplitzB200Error):
+        z = torch.zeros(1 << 25, dtype=torch.float64, device="cuda")
+        z[0] = 1
+        tb.factorize(tb.SymmetricToeplitz(z))          # embedding 2^26 exceeds the Float64 plan: refused, no fallback

@@ -263,9 +263,10 @@ static int make_plan(tb200_fact* h) {
     }
     int l2max = h->prec ? g_l2max_f64.load() : g_l2max_f32.load();
     if (!h->prec && l >= 25 && l2max < 14) l2max = 14;        // 2^25: 2^11 x 2^14 measured 12 % faster than 2^12 x 2^13
+    if (h->prec && l - l2max > 11 && l2max < 13) l2max = 13;  // keep 128-byte... at least 64-byte column tiles as long as possible
     int l1 = std::max(l - l2max, std::min(9, l / 2));
     int l2 = l - l1;
-    const int l1max = h->prec ? 11 : 12;
+    const int l1max = 12;                                    // 2^12 x 2^13 (Float64, 2 columns per tile) / 2^12 x 2^14 (Float32)
     if (l1 > l1max) { l1 = l1max; l2 = l - l1; }
     if (l2 > (h->prec ? 13 : 14))
         return set_error(TB200_UNSUPPORTED, "embedding length 2^%d exceeds the two-level plan (max 2^%d)", l,
@@ -275,7 +276,7 @@ static int make_plan(tb200_fact* h) {
     const int full = 128 / (int)(h->prec ? 16 : 8);            // columns per 128-byte line
     int ta = full;
     const size_t esz = h->prec ? 16 : 8;
-    while (ta > 4 && ((size_t)1 << l1) * ta * esz > 128 * 1024) ta >>= 1;
+    while (ta > 2 && ((size_t)1 << l1) * ta * esz > 128 * 1024) ta >>= 1;
     if (g_ta_cap.load() >= 4 && ta > g_ta_cap.load()) ta = g_ta_cap.load();
     h->two_level = 1; h->log2l1 = l1; h->log2l2 = l2; h->ta = ta;
     // inter-level twiddles  w_Np^m = lo[m & mask] * hi[m >> hb]  (cached per device / precision / length)

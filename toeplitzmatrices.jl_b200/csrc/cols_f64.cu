@@ -11,6 +11,7 @@ namespace tb {
     case 904: return launch_cols_one<double, 9, 4, LAST>(a, s);                    \
     case 1108: return launch_cols_one<double, 11, 8, LAST>(a, s);                  \
     case 1104: return launch_cols_one<double, 11, 4, LAST>(a, s);                  \
+    case 1202: return launch_cols_one<double, 12, 2, LAST>(a, s);                  \
     default: return cudaErrorInvalidValue;                                         \
     }
 template <> cudaError_t launch_colsA<double>(int log2l1, int ta, const ConvArgs<double>& a, cudaStream_t s) { TB_COLS_CASES(false) }
