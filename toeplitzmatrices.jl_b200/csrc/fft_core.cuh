@@ -168,18 +168,6 @@ template <typename R> __device__ __forceinline__ cx<R> ldg_cx(const cx<R>* p) { 
 #ifndef TB_TWGEN_F32
 #define TB_TWGEN_F32 1
 #endif
-// Experiment TB_TW_CHAIN: apply w^c = w^(c-1) * w on the fly (2 live twiddles instead of E) to cut registers.
-template <typename R, int E, int LOGE_, bool CONJ>
-__device__ __forceinline__ void apply_twiddles_chain(const cx<R>* __restrict__ blk, int r, cx<R>* a) {
-    const cx<R> w1 = ldg_cx<R>(blk + r);
-    cx<R> w = w1;
-#pragma unroll
-    for (int c = 1; c < E; ++c) {
-        a[brev(c, LOGE_)] = CONJ ? cmulc(a[brev(c, LOGE_)], w) : cmul(a[brev(c, LOGE_)], w);
-        if (c + 1 < E) w = cmul(w, w1);
-    }
-}
-
 template <typename R, int E>
 __device__ __forceinline__ void stage_twiddles_of_thread(const cx<R>* __restrict__ blk, int s, int r, cx<R>* w) {
     if constexpr ((sizeof(R) == 8 && TB_TWGEN_F64) || (sizeof(R) == 4 && TB_TWGEN_F32)) {
@@ -268,14 +256,10 @@ struct SlotFFT {
             }
             dif_regs<R, E>(a);
             if (ls > 0) {
-#ifdef TB_TW_CHAIN
-                apply_twiddles_chain<R, E, LOGE, false>(tw + stage_tw_off(LOG2L, k, LOGE), r, a);
-#else
                 cx<R> w[E];
                 stage_twiddles_of_thread<R, E>(tw + stage_tw_off(LOG2L, k, LOGE), s, r, w);
 #pragma unroll
                 for (int c = 1; c < E; ++c) a[brev(c, LOGE)] = cmul(a[brev(c, LOGE)], w[c]);
-#endif
             }
             const bool last = (k == NFULL - 1) && (REM == 0);
             if (!last) {
@@ -323,14 +307,10 @@ struct SlotFFT {
                 for (int c = 0; c < E; ++c) TB_SM_LOAD(a[brev(c, LOGE)], sm[map.at(pre, c << ls)]);
             }
             if (ls > 0) {
-#ifdef TB_TW_CHAIN
-                apply_twiddles_chain<R, E, LOGE, true>(tw + stage_tw_off(LOG2L, k, LOGE), r, a);
-#else
                 cx<R> w[E];
                 stage_twiddles_of_thread<R, E>(tw + stage_tw_off(LOG2L, k, LOGE), s, r, w);
 #pragma unroll
                 for (int c = 1; c < E; ++c) a[brev(c, LOGE)] = cmulc(a[brev(c, LOGE)], w[c]);
-#endif
             }
             dit_regs<R, E>(a);
             if (k > 0) {

@@ -106,9 +106,6 @@ struct OutView {
 // occupancy target: 128 registers/thread for Float64, 64 for Float32, limited by shared memory
 template <typename R>
 constexpr int min_ctas(int threads, int smem_bytes) {
-#ifdef TB_EXP_MINCTAS
-    if (sizeof(R) == 8 && threads == 256) return TB_EXP_MINCTAS;
-#endif
     int by_regs = 65536 / (threads * 2 * ((sizeof(R) == 8 ? 4 : 2) << le_of<R>()));   // budget: 2x the data registers
     int by_smem = (220 * 1024) / (smem_bytes > 0 ? smem_bytes : 1);
     int m = by_regs < by_smem ? by_regs : by_smem;
@@ -140,15 +137,6 @@ k_rows(const ConvArgs<R> p) {
     const int slot = threadIdx.x / NT, t = threadIdx.x % NT;
     cx<R>* sm = reinterpret_cast<cx<R>*>(smraw) + slot * L;
     RowMap<R> map;
-#ifdef TB_EXP_SKEW          // experiment: de-phase the two CTAs that share an SM
-    if ((blockIdx.x / 148) & 1) __nanosleep(TB_EXP_SKEW);
-#endif
-#ifdef TB_EXP_STAGGER       // experiment: spread the GPU-wide load bursts by delaying CTAs by SM id
-    {
-        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        if (blockIdx.x < 296) __nanosleep((smid & 7) * TB_EXP_STAGGER);
-    }
-#endif
 
     for (long long f0 = (long long)blockIdx.x * TS; f0 < p.nfft; f0 += (long long)gridDim.x * TS) {
         const long long f = f0 + slot;
@@ -157,12 +145,6 @@ k_rows(const ConvArgs<R> p) {
         cx<R> a[E];
         TB_TRACE(0);
         const cx<R>* srow = p.spec ? p.spec + (fc % p.spec_rows) * (long long)L + t : nullptr;
-#ifdef TB_EXP_PREFETCH_SPEC     // experiment: pull the spectrum row into L1 while the row itself is in flight
-        if (srow) {
-#pragma unroll
-            for (int i = 0; i < E; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(srow + i * NT));
-        }
-#endif
         if (p.x_mode == IO_SPEC) {
             const cx<R>* xin = reinterpret_cast<const cx<R>*>(p.x) + fc * (long long)L + t;
 #pragma unroll
