@@ -205,6 +205,22 @@ function ToeplitzMatrices.levinson!(x::Union{DV{T},DM{T}}, r::Union{DV{T},DM{T}}
     x
 end
 
+# many right-hand sides, one matrix (the column loop of ext/ToeplitzMatricesStatsBaseExt.jl:15-24): the y-recursion runs once
+function ToeplitzMatrices.levinson(A::SymmetricToeplitz{T,<:DV}, B::DM{T}) where {T<:Union{Float32,Float64}}
+    n = size(A, 1)
+    size(B, 1) == n || throw(DimensionMismatch("first dimension of B, $(size(B, 1)), does not match size of A, $n"))
+    X = similar(B)
+    if 2 <= n <= 512
+        check(ccall((:tb200_levinson_multirhs, libtb), Cint,
+                    (Cint, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
+                    dtcode(T), n, size(B, 2), devptr(A.vc), devptr(B), stride(B, 2), devptr(X), stride(X, 2), curstream()))
+        return X
+    end
+    r0 = A.vc[1:1]
+    r = repeat(A.vc[2:end] ./ r0, 1, size(B, 2))
+    ToeplitzMatrices.levinson!(X, r, B, repeat(r0, size(B, 2)))
+end
+
 # ---- trench (src/directLinearSolvers.jl:36-85) and triangular inverse (src/linearalgebra.jl:337-396) ----
 function ToeplitzMatrices.trench(T::SymmetricToeplitz{S,<:DV}) where {S<:Union{Float32,Float64}}
     n = size(T, 1)

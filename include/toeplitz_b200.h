@@ -125,6 +125,12 @@ int tb200_levinson_batched(int dtype, int64_t n, int64_t nsys, const void* r, in
                            void* stream);
 int tb200_durbin_batched(int dtype, int64_t n, int64_t nsys, const void* r, int64_t ldr,
                          void* y, int64_t ldy, void* stream);
+/* Many right-hand sides, ONE matrix: X = SymmetricToeplitz(vc) \ B, the column loop of
+ * ext/ToeplitzMatricesStatsBaseExt.jl:15-24.  The y-recursion of levinson! (src/directLinearSolvers.jl:114-118)
+ * is independent of b: it runs once, the per-column work drops from 5k to 2k FMAs per step.  vc: n entries
+ * (vc[0] = diagonal, :123-134); B, X: n x nrhs; 2 <= n <= 512 (larger n: tb200_levinson_batched).           */
+int tb200_levinson_multirhs(int dtype, int64_t n, int64_t nrhs, const void* vc, const void* B, int64_t ldb,
+                            void* X, int64_t ldx, void* stream);
 
 /* trench(T::SymmetricToeplitz) src/directLinearSolvers.jl:36-85: B (n x n, column-major, ldb) = inv(T) for the
  * SPD matrix T = diag * SymToeplitz([1; r]); r has n-1 entries (already divided by diag, :51-53), real dtype.

@@ -99,6 +99,21 @@ def c5():
         iterations=it, flag=flag, final_rel_residual=err, alg_gbs=19 * n * 8 * it / dt / 1e9)
 
 
+def c4m():
+    """one matrix, many right-hand sides (shared y-recursion) vs the replicated batched kernel"""
+    n, nrhs = 512, 200000
+    a = torch.cat([torch.ones(1, dtype=torch.float64, device="cuda"), torch.rand(n - 1, dtype=torch.float64, device="cuda") / n])
+    T = tb.SymmetricToeplitz(a)
+    B = torch.randn((nrhs, n), dtype=torch.float64, device="cuda").t()
+    t = timed(lambda: tb.levinson(T, B), 3, warm=1)
+    R = a[1:].unsqueeze(1).expand(-1, nrhs)
+    R = tb.to_colmajor(R)
+    X = tb.colmajor(n, nrhs)
+    t2 = timed(lambda: tb.levinson_(X, R, B), 3, warm=1)
+    out(config="C4m SymmetricToeplitz{Float64} n=512, one matrix x 2e5 right-hand sides", shared_recursion_solves_per_s=nrhs / t,
+        replicated_solves_per_s=nrhs / t2)
+
+
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if "=" not in a]
     for kv in (a for a in sys.argv[1:] if "=" in a):       # tuning: library options, e.g. l2max_f64=13

@@ -481,3 +481,16 @@ def test_mul_host_pageable_and_complex(tb):
     tb.mul_host_(Yh, F, Xh, 0.5 - 1j, 2.0)
     ref = (0.5 - 1j) * O.matvec(O.Hankel(v, (n, n)), X) + 2.0 * Y0
     assert rel(Yh.numpy(), ref) <= TOL64
+
+
+@pytest.mark.parametrize("n", [2, 5, 128, 129, 300, 512])
+def test_levinson_multirhs_shared_recursion(tb, n):
+    """levinson(T::SymmetricToeplitz, B::Matrix): one matrix, many right-hand sides (the column loop of
+    ext/ToeplitzMatricesStatsBaseExt.jl:15-24) with the y-recursion tabulated once; vs the C oracle per column."""
+    rng = np.random.default_rng(n)
+    a = 2.5 * np.concatenate([[1.0], rng.random(n - 1) / n])          # non-unit diagonal
+    Bm = np.asfortranarray(rng.standard_normal((n, 33)))
+    X = host(tb.levinson(tb.SymmetricToeplitz(dev(a)), devmat(Bm)))
+    ref = np.stack([OC.c_levinson_sym(a, Bm[:, j]) for j in range(Bm.shape[1])], axis=1)
+    assert rel(X, ref) <= TOL64
+    assert rel(X, np.linalg.solve(O.SymmetricToeplitz(a).dense(), Bm)) <= 1e-10

@@ -21,7 +21,7 @@ EXPORTS = [
     "tb200_circ_spectrum", "tb200_circ_map", "tb200_circ_mul", "tb200_circ_to_vc",
     "tb200_precond_vector", "tb200_levinson_batched", "tb200_durbin_batched", "tb200_cgs", "tb200_cg",
     "tb200_factorize_empty", "tb200_spectrum_buffer", "tb200_launch_count", "tb200_set_option",
-    "tb200_pass_times", "tb200_trench", "tb200_tri_smallinv",
+    "tb200_pass_times", "tb200_trench", "tb200_tri_smallinv", "tb200_levinson_multirhs",
 ]
 
 
@@ -81,6 +81,7 @@ def lib() -> ctypes.CDLL:
         "tb200_pass_times": [pd, pi64],
         "tb200_trench": [ci, i64, vp, vp, i64, dbl, vp],
         "tb200_tri_smallinv": [ci, i64, vp, vp, vp],
+        "tb200_levinson_multirhs": [ci, i64, i64, vp, vp, i64, vp, i64, vp],
     }
     for name, args in sig.items():
         f = getattr(L, name)

@@ -667,6 +667,14 @@ def levinson(r_or_T, b: torch.Tensor) -> torch.Tensor:
     columns as in ext/ToeplitzMatricesStatsBaseExt.jl:15-24)."""
     b = to_colmajor(_floatify(b))
     x = torch.zeros_like(b) if b.dim() == 1 else colmajor(b.shape[0], b.shape[1], b.dtype, b.device)
+    if isinstance(r_or_T, SymmetricToeplitz) and b.dim() == 2 and 2 <= b.shape[0] <= 512 and b.shape[1] >= 2:
+        # many right-hand sides, one matrix: the y-recursion is shared (ext/ToeplitzMatricesStatsBaseExt.jl:15-24)
+        vc = r_or_T.vc.to(b.dtype).contiguous()
+        if vc.shape[0] != b.shape[0]:
+            raise DimensionMismatch("length(b) = %d != %d = size(T, 1)" % (b.shape[0], vc.shape[0]))
+        check(L.lib().tb200_levinson_multirhs(_DT[b.dtype], b.shape[0], b.shape[1], vc.data_ptr(), b.data_ptr(), _ld(b),
+                                              x.data_ptr(), _ld(x), _stream()))
+        return x
     if isinstance(r_or_T, SymmetricToeplitz):
         T = r_or_T
         l = _ncols(b)

@@ -1081,6 +1081,22 @@ int tb200_durbin_batched(int dtype, int64_t n, int64_t nsys, const void* r, int6
     return levinson_dispatch(dtype, true, n, nsys, r, ldr, nullptr, 0, y, ldy, nullptr, (cudaStream_t)stream);
 }
 
+int tb200_levinson_multirhs(int dtype, int64_t n, int64_t nrhs, const void* vc, const void* B, int64_t ldb, void* X, int64_t ldx,
+                            void* stream) {
+    if (n <= 0 || nrhs < 0) return set_error(TB200_BAD_ARG, "bad sizes");
+    if (nrhs == 0) return TB200_OK;
+    if (!vc || !B || !X) return set_error(TB200_BAD_ARG, "NULL argument");
+    if (ldb < n || ldx < n) return set_error(TB200_DIM_MISMATCH, "B and X must have %lld rows", (long long)n);
+    if (dtype != TB200_F32 && dtype != TB200_F64) return set_error(TB200_UNSUPPORTED, "levinson: only real Float32/Float64 systems");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t esz = dt_prec(dtype) ? 8 : 4;
+    std::shared_ptr<DevBuf> work;
+    TB_TRY(dev_alloc(work, esz * (size_t)(n * ((n + 127) / 128 * 128) + 2 * n + 8), "levinson y-table"));
+    TB_TRY(levinson_multirhs_dispatch(dtype, n, nrhs, vc, B, ldb, X, ldx, work->p, s));
+    TB_CUDA(cudaStreamSynchronize(s), "levinson multi-RHS sync");     // the table is released on return
+    return TB200_OK;
+}
+
 int tb200_tri_smallinv(int dtype, int64_t n, const void* v, void* out, void* stream) {
     if (!dt_valid(dtype)) return set_error(TB200_BAD_ARG, "unknown dtype");
     if (n < 1 || n > 64) return set_error(TB200_BAD_ARG, "smallinv is the n <= 64 base case, got n = %lld", (long long)n);

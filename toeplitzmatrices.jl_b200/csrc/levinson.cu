@@ -297,6 +297,206 @@ static int launch_levinson(int64_t n, int64_t nsys, const R* r, int64_t ldr, con
     return cuda_status(cudaGetLastError(), "levinson block kernel");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Many right-hand sides, ONE matrix (the shape of ext/ToeplitzMatricesStatsBaseExt.jl:15-24): the y-recursion
+// (Durbin part of levinson!, src/directLinearSolvers.jl:114-118) does not depend on b, so it runs once and
+// tabulates, for every order k, 1/beta_k and reverse(y_k); each right-hand side then only needs
+//   mu = (b[k+1] - reverse_dot(r_k, x_k)) / beta ;  x_k += mu*reverse(y_k) ;  x[k+1] = mu      (:111-113)
+// i.e. 2k instead of 5k FMAs per step, one warp per right-hand side, x in registers as above.
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, int S, int SC, int J>
+__device__ __forceinline__ void ytab_step(LevState<R, S>& st, int k, int n, int lane, int lb, const R* r_s,
+                                          R* __restrict__ ytab, R* __restrict__ ibeta_tab) {
+    constexpr int ACT = (SC + 1) * LB;
+    constexpr int PH = (J + LB - 1) & (LB - 1);
+    st.beta *= ((R)1 - st.alpha * st.alpha);
+    const R ibeta = fast_rcp(st.beta);
+    if (lane == 0) ibeta_tab[k] = ibeta;
+    // reverse(y_k) in natural order, zero padded to the active super-rows, at row k of a (n x S*128) table:
+    // rows are 16-byte aligned so the consumers read them with unconditional 128-bit loads
+    R* row = ytab + (long long)k * (S * LSPAN);
+#pragma unroll
+    for (int i = 0; i < ACT; ++i) row[(i / LB) * LSPAN + lane * LB + (i % LB)] = st.yh[phys(i, PH)];
+    if (k < n - 1) {
+        R p2[LB];
+#pragma unroll
+        for (int q = 0; q < LB; ++q) p2[q] = 0;
+#pragma unroll
+        for (int i = 0; i < ACT; ++i) p2[i % LB] = fma(st.rh[phys(i, PH)], st.y[i], p2[i % LB]);
+        const R d2 = warp_sum((p2[0] + p2[1]) + (p2[2] + p2[3]));
+        const R rk = r_s[k];
+        st.alpha = -(rk + d2) * ibeta;
+#pragma unroll
+        for (int i = 0; i < ACT; ++i) {
+            const R yo = st.y[i];
+            st.y[i] = fma(st.alpha, st.yh[phys(i, PH)], yo);
+            st.yh[phys(i, PH)] = fma(st.alpha, yo, st.yh[phys(i, PH)]);
+        }
+        if (lane == lb) st.y[SC * LB + J] = st.alpha;
+        shift_up<R, SC + 1, PH>(st.yh, st.alpha, lane);
+        shift_up<R, SC + 1, PH>(st.rh, rk, lane);
+    }
+}
+
+template <typename R, int S, int SC>
+__device__ __forceinline__ void ytab_superrows(LevState<R, S>& st, int n, int lane, const R* r_s, R* ytab, R* ibeta_tab) {
+    if constexpr (SC < S) {
+        for (int lb = 0; lb < 32; ++lb) {
+            const int k0 = SC * LSPAN + lb * LB;
+            if (k0 >= n) break;
+            if (k0 + 0 >= 1 && k0 + 0 < n) ytab_step<R, S, SC, 0>(st, k0 + 0, n, lane, lb, r_s, ytab, ibeta_tab);
+            if (k0 + 1 < n) ytab_step<R, S, SC, 1>(st, k0 + 1, n, lane, lb, r_s, ytab, ibeta_tab);
+            if (k0 + 2 < n) ytab_step<R, S, SC, 2>(st, k0 + 2, n, lane, lb, r_s, ytab, ibeta_tab);
+            if (k0 + 3 < n) ytab_step<R, S, SC, 3>(st, k0 + 3, n, lane, lb, r_s, ytab, ibeta_tab);
+        }
+        ytab_superrows<R, S, SC + 1>(st, n, lane, r_s, ytab, ibeta_tab);
+    }
+}
+
+// one warp: the shared y-recursion of T = SymToeplitz(vc) (n x n); rnorm receives r = vc[1:] / vc[0]
+template <typename R, int S>
+__global__ void __launch_bounds__(32)
+k_levinson_ytab(int n, const R* __restrict__ vc, R* __restrict__ rnorm, R* __restrict__ ytab, R* __restrict__ ibeta_tab) {
+    __shared__ R r_s[S * LSPAN];
+    const int lane = threadIdx.x;
+    const R d = vc[0];
+    for (int i = lane; i < n - 1; i += 32) { const R v = (d != (R)1) ? vc[i + 1] / d : vc[i + 1]; r_s[i] = v; rnorm[i] = v; }
+    __syncwarp();
+    LevState<R, S> st;
+#pragma unroll
+    for (int i = 0; i < S * LB; ++i) { st.x[i] = 0; st.y[i] = 0; st.yh[i] = 0; st.rh[i] = 0; }
+    const R r0 = r_s[0];
+    if (lane == 0) { st.y[0] = -r0; st.yh[0] = -r0; st.rh[0] = r0; }
+    st.alpha = -r0;
+    st.beta = (R)1;
+    ytab_superrows<R, S, 0>(st, n, lane, r_s, ytab, ibeta_tab);
+}
+
+// two right-hand sides per warp: the tabulated reverse(y_k) and the shifting r-window are loaded / kept once and
+// used twice, and the two dot products share one fused two-value reduction
+template <typename R, int S, int SC, int J>
+__device__ __forceinline__ void rhs_step(R* xa, R* xb, R* rh, int k, int n, int lane, int lb, const R* r_s, const R* ba_s,
+                                         const R* bb_s, const R* __restrict__ ytab, const R* __restrict__ ibeta_tab) {
+    constexpr int ACT = (SC + 1) * LB;
+    constexpr int PH = (J + LB - 1) & (LB - 1);
+    // reverse(y_k) for this lane's slots: independent of the reduction, so the loads are in flight during it
+    const R* row = ytab + (long long)k * (S * LSPAN) + lane * LB;
+    R yh[ACT];
+#pragma unroll
+    for (int sr = 0; sr <= SC; ++sr) {
+        if constexpr (sizeof(R) == 8) {
+            const double2 v0 = __ldg(reinterpret_cast<const double2*>(row + sr * LSPAN));
+            const double2 v1 = __ldg(reinterpret_cast<const double2*>(row + sr * LSPAN) + 1);
+            yh[sr * LB + 0] = v0.x; yh[sr * LB + 1] = v0.y; yh[sr * LB + 2] = v1.x; yh[sr * LB + 3] = v1.y;
+        } else {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(row + sr * LSPAN));
+            yh[sr * LB + 0] = v.x; yh[sr * LB + 1] = v.y; yh[sr * LB + 2] = v.z; yh[sr * LB + 3] = v.w;
+        }
+    }
+    const R ibeta = __ldg(ibeta_tab + k);
+    R pa[LB], pb[LB];
+#pragma unroll
+    for (int q = 0; q < LB; ++q) { pa[q] = 0; pb[q] = 0; }
+#pragma unroll
+    for (int i = 0; i < ACT; ++i) {
+        pa[i % LB] = fma(rh[phys(i, PH)], xa[i], pa[i % LB]);
+        pb[i % LB] = fma(rh[phys(i, PH)], xb[i], pb[i % LB]);
+    }
+    R da = (pa[0] + pa[1]) + (pa[2] + pa[3]);
+    R db = (pb[0] + pb[1]) + (pb[2] + pb[3]);
+    warp_sum2(da, db, lane);
+    const R mua = (ba_s[k] - da) * ibeta;
+    const R mub = (bb_s[k] - db) * ibeta;
+#pragma unroll
+    for (int i = 0; i < ACT; ++i) { xa[i] = fma(mua, yh[i], xa[i]); xb[i] = fma(mub, yh[i], xb[i]); }
+    if (lane == lb) { xa[SC * LB + J] = mua; xb[SC * LB + J] = mub; }
+    if (k < n - 1) shift_up<R, SC + 1, PH>(rh, r_s[k], lane);
+}
+
+template <typename R, int S, int SC>
+__device__ __forceinline__ void rhs_superrows(R* xa, R* xb, R* rh, int n, int lane, const R* r_s, const R* ba_s, const R* bb_s,
+                                              const R* ytab, const R* ibeta_tab) {
+    if constexpr (SC < S) {
+        for (int lb = 0; lb < 32; ++lb) {
+            const int k0 = SC * LSPAN + lb * LB;
+            if (k0 >= n) break;
+            if (k0 + 0 >= 1 && k0 + 0 < n) rhs_step<R, S, SC, 0>(xa, xb, rh, k0 + 0, n, lane, lb, r_s, ba_s, bb_s, ytab, ibeta_tab);
+            if (k0 + 1 < n) rhs_step<R, S, SC, 1>(xa, xb, rh, k0 + 1, n, lane, lb, r_s, ba_s, bb_s, ytab, ibeta_tab);
+            if (k0 + 2 < n) rhs_step<R, S, SC, 2>(xa, xb, rh, k0 + 2, n, lane, lb, r_s, ba_s, bb_s, ytab, ibeta_tab);
+            if (k0 + 3 < n) rhs_step<R, S, SC, 3>(xa, xb, rh, k0 + 3, n, lane, lb, r_s, ba_s, bb_s, ytab, ibeta_tab);
+        }
+        rhs_superrows<R, S, SC + 1>(xa, xb, rh, n, lane, r_s, ba_s, bb_s, ytab, ibeta_tab);
+    }
+}
+
+// one warp per PAIR of right-hand side columns; X = T \ B with the tabulated y-recursion; diag = vc[0]
+template <typename R, int S>
+__global__ void __launch_bounds__(128, 3)
+k_levinson_rhs(int n, int64_t nrhs, const R* __restrict__ rnorm, const R* __restrict__ vc, const R* __restrict__ Bm, int64_t ldb,
+               R* __restrict__ Xm, int64_t ldx, const R* __restrict__ ytab, const R* __restrict__ ibeta_tab) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const int64_t cola = 2 * ((int64_t)blockIdx.x * (blockDim.x >> 5) + wic);
+    if (cola >= nrhs) return;
+    const bool two = cola + 1 < nrhs;
+    const int64_t colb = two ? cola + 1 : cola;
+    R* r_s = reinterpret_cast<R*>(smraw) + (size_t)wic * (3 * S * LSPAN);
+    R* ba_s = r_s + S * LSPAN;
+    R* bb_s = ba_s + S * LSPAN;
+    for (int i = lane; i < n - 1; i += 32) r_s[i] = rnorm[i];
+    for (int i = lane; i < n; i += 32) { ba_s[i] = Bm[cola * ldb + i]; bb_s[i] = Bm[colb * ldb + i]; }
+    __syncwarp();
+    R xa[S * LB], xb[S * LB], rh[S * LB];
+#pragma unroll
+    for (int i = 0; i < S * LB; ++i) { xa[i] = 0; xb[i] = 0; rh[i] = 0; }
+    if (lane == 0) { xa[0] = ba_s[0]; xb[0] = bb_s[0]; rh[0] = r_s[0]; }
+    rhs_superrows<R, S, 0>(xa, xb, rh, n, lane, r_s, ba_s, bb_s, ytab, ibeta_tab);
+    const R d = vc[0];
+    R* outa = Xm + cola * ldx;
+    R* outb = Xm + colb * ldx;
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int j = 0; j < LB; ++j) {
+            const int i = s * LSPAN + lane * LB + j;
+            if (i < n) {
+                outa[i] = (d != (R)1) ? xa[s * LB + j] / d : xa[s * LB + j];
+                if (two) outb[i] = (d != (R)1) ? xb[s * LB + j] / d : xb[s * LB + j];
+            }
+        }
+}
+
+template <typename R>
+static int launch_levinson_multirhs(int64_t n, int64_t nrhs, const R* vc, const R* B, int64_t ldb, R* X, int64_t ldx,
+                                    R* work /* n*S*128 + n + n */, cudaStream_t s) {
+    const int S = (int)((n + LSPAN - 1) / LSPAN);
+    R* ytab = work;                                   // first: keeps the table rows 16-byte aligned
+    R* ibeta_tab = ytab + n * (int64_t)(S * LSPAN);
+    R* rnorm = ibeta_tab + n;
+    const int wpc = 4;
+    const int64_t npairs = (nrhs + 1) / 2;
+    const unsigned grid = (unsigned)((npairs + wpc - 1) / wpc);
+    const size_t smem = (size_t)wpc * 3 * S * LSPAN * sizeof(R);
+#define TB_MR_CASE(SV)                                                                                                   \
+    case SV:                                                                                                             \
+        k_levinson_ytab<R, SV><<<1, 32, 0, s>>>((int)n, vc, rnorm, ytab, ibeta_tab);                                    \
+        k_levinson_rhs<R, SV><<<grid, wpc * 32, smem, s>>>((int)n, nrhs, rnorm, vc, B, ldb, X, ldx, ytab, ibeta_tab);  \
+        break;
+    switch (S) { TB_MR_CASE(1) TB_MR_CASE(2) TB_MR_CASE(3) TB_MR_CASE(4) }
+#undef TB_MR_CASE
+    count_launch(2);
+    return cuda_status(cudaGetLastError(), "multi-RHS levinson kernels");
+}
+
+int levinson_multirhs_dispatch(int dtype, int64_t n, int64_t nrhs, const void* vc, const void* B, int64_t ldb, void* X,
+                               int64_t ldx, void* work, cudaStream_t s) {
+    if (n < 2 || n > 4 * LSPAN) return set_error(TB200_UNSUPPORTED, "multi-RHS levinson: 2 <= n <= 512 (use tb200_levinson_batched)");
+    if (dtype == TB200_F64) return launch_levinson_multirhs<double>(n, nrhs, (const double*)vc, (const double*)B, ldb, (double*)X, ldx, (double*)work, s);
+    if (dtype == TB200_F32) return launch_levinson_multirhs<float>(n, nrhs, (const float*)vc, (const float*)B, ldb, (float*)X, ldx, (float*)work, s);
+    return set_error(TB200_UNSUPPORTED, "levinson: only real Float32/Float64 systems");
+}
+
 int levinson_dispatch(int dtype, bool durbin, int64_t n, int64_t nsys, const void* r, int64_t ldr, const void* b,
                       int64_t ldb, void* x, int64_t ldx, const void* diag, cudaStream_t s) {
     if (dtype == TB200_F64) {
