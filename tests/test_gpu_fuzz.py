@@ -1,0 +1,160 @@
+"""Seeded random-shape parity sweep of `mul!` through the C ABI against the CPU oracle.
+
+The reference's tests use a handful of sizes (test/runtests.jl:23-95, 154-215); the CUDA path has more
+regimes than the FFTW path has (direct product for N < 512, one shared-memory transform, two-level
+transform, chirp-z for non-power-of-two circulants, two real columns packed per transform, odd column
+tails, padded leading dimensions, alpha/beta epilogue), so this sweep draws sizes log-uniformly across
+all of them.  Tolerances: relative 2-norm error 1e-12 (Float64 family) / 1e-5 (Float32 family)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import toeplitz_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ["toeplitz", "symmetric", "circulant", "lower", "upper", "hankel"]
+DTYPES = [np.float64, np.complex128, np.float32, np.complex64]
+
+
+@pytest.fixture(scope="module")
+def tb():
+    import toeplitz_b200 as tb
+    return tb
+
+
+def _rand(rng, shape, dtype):
+    dt = np.dtype(dtype)
+    a = rng.standard_normal(shape)
+    if dt.kind == "c":
+        a = a + 1j * rng.standard_normal(shape)
+    return a.astype(dt)
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _devmat_padded(a, pad):
+    """numpy (n, l) -> column-major CUDA view (n, l) whose leading dimension is n + pad."""
+    n, l = a.shape
+    big = torch.full((l, n + pad), float("nan"), dtype=torch.from_numpy(a[:0]).dtype, device="cuda")
+    big[:, :n] = torch.from_numpy(np.ascontiguousarray(a.T)).cuda()
+    return big.t()[:n, :]
+
+
+def _rel(a, b):
+    den = np.linalg.norm(b.ravel())
+    return np.linalg.norm((a - b).ravel()) / (den if den > 0 else 1.0)
+
+
+def _size(rng, hi):
+    return int(np.exp(rng.uniform(0.0, np.log(hi))))
+
+
+def _build(tb, rng, kind, dtype, hi):
+    n = max(1, _size(rng, hi))
+    if kind == "toeplitz":
+        m = max(1, _size(rng, hi)) if rng.random() < 0.5 else n
+        vc, vr = _rand(rng, m, dtype), _rand(rng, n, dtype)
+        vr[0] = vc[0]
+        return O.Toeplitz(vc, vr), tb.Toeplitz(_dev(vc), _dev(vr)), m, n
+    if kind == "hankel":
+        m = max(1, _size(rng, hi)) if rng.random() < 0.5 else n
+        v = _rand(rng, m + n - 1, dtype)
+        return O.Hankel(v, size=(m, n)), tb.Hankel(_dev(v), size=(m, n)), m, n
+    v = _rand(rng, n, dtype)
+    cls = {"symmetric": "SymmetricToeplitz", "circulant": "Circulant", "lower": "LowerTriangularToeplitz",
+           "upper": "UpperTriangularToeplitz"}[kind]
+    return getattr(O, cls)(v), getattr(tb, cls)(_dev(v)), n, n
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_mul_random_shapes(tb, seed):
+    rng = np.random.default_rng(1000 + seed)
+    for case in range(14):
+        kind = KINDS[int(rng.integers(len(KINDS)))]
+        dtype = DTYPES[int(rng.integers(len(DTYPES)))]
+        single = np.dtype(dtype) in (np.dtype(np.float32), np.dtype(np.complex64))
+        hi = 70000 if case % 7 == 0 else 6000          # a few cases reach the two-level transform
+        Ao, Ad, m, n = _build(tb, rng, kind, dtype, hi)
+        rdt = np.zeros(1, dtype).real.dtype
+        cdt = np.result_type(dtype, np.complex64)
+        xdt = cdt if rng.random() < 0.4 else rdt
+        ncols = int(rng.integers(1, 8))
+        tol = 1e-5 if single else 1e-12
+        tag = "seed %d case %d: %s %s m=%d n=%d cols=%d x=%s" % (seed, case, kind, np.dtype(dtype).name, m, n, ncols,
+                                                                np.dtype(xdt).name)
+        X = _rand(rng, (n, ncols), xdt)
+        want = O.matvec(Ao, X)
+        # plain product, padded leading dimension on the input
+        got = tb.mul(Ad, _devmat_padded(X, int(rng.integers(0, 9)))).cpu().numpy()
+        assert _rel(got, want) <= tol, tag
+        # vector form (takes the direct product when m + n - 1 < 512, src/linearalgebra.jl:19-34)
+        gv = tb.mul(Ad, _dev(X[:, 0].copy())).cpu().numpy()
+        assert _rel(gv, want[:, 0]) <= tol, tag + " (vector)"
+        # alpha / beta epilogue into a padded y through a factorization (src/linearalgebra.jl:42-80)
+        ydt = want.dtype
+        alpha = float(rng.standard_normal())
+        beta = float(rng.standard_normal())
+        Y0 = _rand(rng, (m, ncols), ydt)
+        Yd = _devmat_padded(Y0, int(rng.integers(0, 9)))
+        F = tb.factorize(Ad)
+        tb.mul_(Yd, F, _devmat_padded(X, 0), alpha, beta)
+        ref = alpha * want + beta * Y0
+        assert _rel(Yd.cpu().numpy(), ref) <= 4 * tol, tag + " (alpha, beta)"
+        # the padding rows of y were not touched
+        base = Yd._base if Yd._base is not None else Yd
+        assert bool(torch.isnan(torch.view_as_real(base) if base.is_complex() else base).any()) == (Yd.stride(1) > m), tag
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_circulant_solves_random_sizes(tb, seed):
+    """ldiv!/inv/eigvals of Circulant (src/linearalgebra.jl:225-253,286-287) at random sizes: power-of-two plans
+    (one-level and two-level) and chirp-z plans."""
+    rng = np.random.default_rng(2000 + seed)
+    for case in range(10):
+        dtype = [np.float64, np.complex128, np.complex64][int(rng.integers(3))]
+        single = np.dtype(dtype) == np.dtype(np.complex64)
+        n = max(1, _size(rng, 40000))
+        if case % 3 == 0:
+            n = 1 << int(rng.integers(0, 16))
+        tol = 2e-4 if single else 1e-10        # ldiv divides by the spectrum: conditioning enters, see below
+        v = _rand(rng, n, dtype)
+        v[0] += 4.0 * np.sqrt(n)               # keep the spectrum away from zero (|eig| >= ~sqrt(n))
+        Co, Cd = O.Circulant(v), tb.Circulant(_dev(v))
+        ncols = int(rng.integers(1, 6))
+        B = _rand(rng, (n, ncols), dtype)
+        Bo = np.asfortranarray(B.copy())
+        O.ldiv_mat(Co, Bo, O.circ_ldiv)
+        Bd = _devmat_padded(B, int(rng.integers(0, 5)))
+        tb.ldiv_(Cd, Bd)
+        tag = "seed %d case %d: %s n=%d cols=%d" % (seed, case, np.dtype(dtype).name, n, ncols)
+        assert _rel(Bd.cpu().numpy(), Bo) <= tol, tag
+        assert _rel(tb.eigvals(Cd).cpu().numpy(), np.fft.fft(v.astype(np.complex128))) <= tol, tag + " (eigvals)"
+        assert _rel(tb.inv(Cd).vc.cpu().numpy(), O.circ_inv(Co).vc) <= tol, tag + " (inv)"
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_levinson_durbin_random_sizes(tb, seed):
+    """Batched levinson!/durbin! (src/directLinearSolvers.jl:15-28,100-134) at random orders and batch sizes,
+    warp kernel (n <= 512) and block kernel (n > 512), against the C oracle."""
+    from oracle import build_oracle as OC
+    rng = np.random.default_rng(3000 + seed)
+    for case in range(8):
+        n = max(2, _size(rng, 1500))
+        nsys = int(rng.integers(1, 70))
+        R = np.asfortranarray(rng.random((n, nsys)) / n)
+        Bm = np.asfortranarray(rng.standard_normal((n, nsys)))
+        tag = "seed %d case %d: n=%d nsys=%d" % (seed, case, n, nsys)
+        Y = tb.durbin(_devmat_padded(R, int(rng.integers(0, 4)))).cpu().numpy()
+        assert _rel(Y, OC.c_durbin_batched(R)) <= 1e-12, tag + " (durbin)"
+        Rl = np.asfortranarray(R[: n - 1, :])
+        X = tb.colmajor(n, nsys)
+        tb.levinson_(X, _devmat_padded(Rl, int(rng.integers(0, 4))), _devmat_padded(Bm, int(rng.integers(0, 4))))
+        assert _rel(X.cpu().numpy(), OC.c_levinson_batched(Rl, Bm)) <= 1e-12, tag + " (levinson)"
+        if n <= 512:                              # one matrix, many right-hand sides
+            vc = np.concatenate([[1.7], 1.7 * R[: n - 1, 0]])
+            Xm = tb.levinson(tb.SymmetricToeplitz(_dev(vc)), _devmat_padded(Bm, 0)).cpu().numpy()
+            Rrep = np.asfortranarray(np.repeat(Rl[:, :1], nsys, axis=1))
+            assert _rel(Xm, OC.c_levinson_batched(Rrep, Bm) / 1.7) <= 1e-12, tag + " (multi-rhs)"
