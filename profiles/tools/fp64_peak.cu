@@ -61,6 +61,11 @@ int main() {
     printf("SMs %d, clock %d kHz\n", sms, clk);
     for (int w : {128, 256, 512, 1024})
         printf("FP64 FMA ILP8  %4d thr x2 CTA/SM: %.2f TFLOP/s\n", w, run<double, 8>(sms, 2, w, 20000));
+    // occupancy x ILP sweep: how many independent FP64 FMAs per SM sub-partition the pipe needs
+    for (int w : {128, 256, 512, 1024}) {
+        printf("FP64 FMA %4d thr/SM: ILP1 %.2f  ILP2 %.2f  ILP4 %.2f  ILP8 %.2f TFLOP/s\n", w, run<double, 1>(sms, 1, w, 40000),
+               run<double, 2>(sms, 1, w, 40000), run<double, 4>(sms, 1, w, 20000), run<double, 8>(sms, 1, w, 20000));
+    }
     printf("FP64 FMA ILP16 512 thr x2: %.2f TFLOP/s\n", run<double, 16>(sms, 2, 512, 10000));
     printf("FP32 FMA ILP8  1024 thr x2: %.2f TFLOP/s\n", run<float, 8>(sms, 2, 1024, 40000));
     // shared memory: 16 B per lane loads+stores
