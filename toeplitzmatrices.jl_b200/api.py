@@ -241,6 +241,8 @@ def adjoint(A):
         return UpperTriangularToeplitz(A.v.conj().resolve_conj())
     if isinstance(A, UpperTriangularToeplitz):
         return LowerTriangularToeplitz(A.v.conj().resolve_conj())
+    if isinstance(A, Hankel):                       # src/hankel.jl:113
+        return Hankel(A.v.conj().resolve_conj(), (A.shape[1], A.shape[0]))
     raise TypeError(type(A))
 
 
@@ -255,6 +257,8 @@ def transpose(A):
         return UpperTriangularToeplitz(A.v)
     if isinstance(A, UpperTriangularToeplitz):
         return LowerTriangularToeplitz(A.v)
+    if isinstance(A, Hankel):                       # src/hankel.jl:112
+        return Hankel(A.v, (A.shape[1], A.shape[0]))
     raise TypeError(type(A))
 
 
