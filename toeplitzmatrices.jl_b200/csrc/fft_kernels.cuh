@@ -37,11 +37,12 @@ struct ConvArgs {
     cx<R>* scratch;           // nfft * Np complex
     int log2n2;               // N2 = contiguous (row) length
     const cx<R>* tw_lo; const cx<R>* tw_hi; int tw_hb;   // w_Np^m = lo[m & mask] * hi[m >> hb]
-    const cx<R>* tw_g;        // [E][N2]: w_Np^(delta_i * j2), delta_i = frequency offset of register i (thread-independent)
+    const cx<R>* tw_g;        // [E][N2]: w_Np^(delta_i * j2), delta_i = frequency offset of register i (thread-independent);
+                              // the kernels read rows i = 2^b only and build the rest as subset products
 };
 
 // Inter-level twiddles of one thread (fixed column j2): w^(k1(i) j2) = w^(kbase(t) j2) * w^(delta_i j2).
-// One split-table lookup for the base, E coalesced loads from the [E][N2] table, E complex multiplies.
+// One split-table lookup for the base, LOGE coalesced loads from the [E][N2] table, E-1 complex multiplies.
 template <typename R, class F>
 __device__ __forceinline__ void level_twiddles(const ConvArgs<R>& p, int t, int j2, cx<R>* w);
 
@@ -206,9 +207,17 @@ template <typename R, class F>
 __device__ __forceinline__ void level_twiddles(const ConvArgs<R>& p, int t, int j2, cx<R>* w) {
     const unsigned kbase = (unsigned)F::freq_of_pos(F::pos_of_reg(0, t));
     const cx<R> base = level_twiddle<R>(p, kbase * (unsigned)j2);
+    // delta_i is linear in the bits of i (pos_of_reg and freq_of_pos move disjoint bit fields), so the E factors
+    // w^(delta_i j2) are the subset products of LOGE generators: LOGE table loads and E-1 multiplies instead of E loads
+    // and E multiplies -- the table rows were as much L2 traffic as the tile itself
     const cx<R>* g = p.tw_g + j2;
+    w[0] = base;
 #pragma unroll
-    for (int i = 0; i < F::E; ++i) w[i] = cmul(base, __ldg(g + ((long long)i << p.log2n2)));
+    for (int b = 0; b < F::LOGE; ++b) {
+        const cx<R> gb = __ldg(g + ((long long)(1 << b) << p.log2n2));
+#pragma unroll
+        for (int i = (1 << b); i < (2 << b); ++i) w[i] = cmul(w[i - (1 << b)], gb);
+    }
 }
 
 // grid.x = (N2/TA) * nfft ; block = TA * NT1
