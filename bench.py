@@ -22,6 +22,7 @@ from __future__ import annotations
 import argparse
 import concurrent.futures as cf
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -314,6 +315,13 @@ def run_ours(args):
                 "timed_how": "CUDA events around every pass on its launching stream, second K-step region, overlap off",
                 "whole_step_frac": ALG_BYTES_PER_MATVEC * ncols / (ms / args.steps * 1e-3) / 1e9 / peak,
                 "co_bound": "FP64 FMA pipe: ~210 MFLOP per matvec (SURVEY 8d)"}
+    # the same step seen from the FP64 pipe: nominal 5 N log2 N flops per complex transform of N = 2^21, two transforms
+    # per column pair; peak = FMA throughput measured on this pool (profiles/tools/fp64_peak.cu), of which an FFT's
+    # add-dominated butterflies can use about half
+    fp64_flop_per_matvec = 5.0 * (2 * n) * math.log2(2 * n)
+    fp64_tflops = fp64_flop_per_matvec * ncols / (ms / args.steps * 1e-3) / 1e12
+    roofline["fp64"] = {"flop_per_matvec": fp64_flop_per_matvec, "achieved_tflops": fp64_tflops, "peak_tflops": 33.7,
+                        "frac": fp64_tflops / 33.7}
 
     # ---- CPU baseline on a bounded sample of the same workload, rank 0 only
     cpu = None
