@@ -187,6 +187,31 @@ ldiv!(A::SymmetricToeplitz{T,<:DV}, b::DV) where {T} =
 ldiv!(A::TriangularToeplitz{T,<:DV}, b::DV) where {T} =
     copyto!(b, IterativeLinearSolvers.cgs(factorize(A), fill!(similar(b), 0), b, factorize(ToeplitzMatrices.chan(A)), 1000, 100eps())[1])
 
+# matrix right-hand sides (src/linearalgebra.jl:102-110 is a serial column loop): all columns iterate together
+function _krylov_batched(sym, A, X::DM{T}, B::DM{T}, M, max_it, tol) where {T}
+    FA = A isa B200ToeplitzFactorization ? A : factorize(A)
+    FM = M === nothing ? nothing : (M isa B200ToeplitzFactorization ? M : factorize(M))
+    l = size(B, 2)
+    err = zeros(Cdouble, l); it = zeros(Cint, l); flag = zeros(Cint, l)
+    check(ccall((sym, libtb), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint, Int64, Int64, Cint, Cdouble,
+                 Ptr{Cdouble}, Ptr{Cint}, Ptr{Cint}, Ptr{Cvoid}),
+                FA.handle, FM === nothing ? C_NULL : FM.handle, devptr(X), stride(X, 2), devptr(B), stride(B, 2), dtcode(T),
+                size(B, 1), l, max_it, tol, err, it, flag, curstream()))
+    return X, err, it, flag
+end
+function ldiv!(A::Toeplitz{T,<:DV,<:DV}, B::DM) where {T}
+    size(A, 1) == size(A, 2) || error("Division: Rectangular case is not supported.")
+    copyto!(B, _krylov_batched(:tb200_cgs_batched, A, fill!(similar(B), 0), B, ToeplitzMatrices.strang(A), 1000, 100eps())[1])
+end
+function ldiv!(A::SymmetricToeplitz{T,<:DV}, B::DM{Float64}) where {T}
+    X, _, _, flag = _krylov_batched(:tb200_cg_batched, A, fill!(similar(B), 0), B, ToeplitzMatrices.strang(A), 1000, 100eps())
+    any(==(2), flag) && throw(MethodError(copyto!, (B, nothing)))     # the reference's cg returned nothing for that column
+    copyto!(B, X)
+end
+ldiv!(A::TriangularToeplitz{T,<:DV}, B::DM) where {T} =
+    copyto!(B, _krylov_batched(:tb200_cgs_batched, A, fill!(similar(B), 0), B, ToeplitzMatrices.chan(A), 1000, 100eps())[1])
+
 # ---- batched Levinson / Durbin (src/directLinearSolvers.jl:8-28, 93-134) ------------------------------
 function ToeplitzMatrices.durbin!(y::Union{DV{T},DM{T}}, r::Union{DV{T},DM{T}}) where {T<:Union{Float32,Float64}}
     size(y, 1) == size(r, 1) || throw(DimensionMismatch("length(y) = $(size(y, 1)) ≠ $(size(r, 1)) = length(r)"))

@@ -153,6 +153,19 @@ int tb200_cgs(tb200_handle_t A, tb200_handle_t M, void* x, const void* b, int dt
 int tb200_cg(tb200_handle_t A, tb200_handle_t M, void* x, const void* b, int dtype, int64_t n,
              int max_it, double tol, double* err, int* iter, int* flag, void* stream);
 
+/* The matrix forms ldiv!(A, B::Matrix) src/linearalgebra.jl:102-110 (a serial column loop over the
+ * solvers above) with all columns iterating together: X (in: start vectors, out: solutions) and
+ * B are n x nrhs, column-major.  Per column the arithmetic is that of tb200_cgs / tb200_cg; a
+ * column that converges, breaks down (cgs, rho == 0) or returns early is frozen while the others
+ * go on.  err, iter, flag: host arrays of nrhs entries (flag 2 = cg's value-less early return,
+ * src/iterativeLinearSolvers.jl:57-59).  Synchronous on `stream`.                              */
+int tb200_cgs_batched(tb200_handle_t A, tb200_handle_t M, void* X, int64_t ldx, const void* B, int64_t ldb,
+                      int dtype, int64_t n, int64_t nrhs, int max_it, double tol, double* err, int* iter,
+                      int* flag, void* stream);
+int tb200_cg_batched(tb200_handle_t A, tb200_handle_t M, void* X, int64_t ldx, const void* B, int64_t ldb,
+                     int dtype, int64_t n, int64_t nrhs, int max_it, double tol, double* err, int* iter,
+                     int* flag, void* stream);
+
 /* ---- multi-GPU plumbing ----------------------------------------------------------------
  * The only exchange on the path is the spectrum, once per factorization: rank 0
  * factorizes, the other ranks create an empty handle of the same shape and the caller

@@ -114,6 +114,36 @@ def c4m():
         replicated_solves_per_s=nrhs / t2)
 
 
+def c6():
+    """Toeplitz \\ B with many right-hand sides: batched cgs + Strang vs the reference's column loop of single solves."""
+    for n, l in ((1 << 16, 256), (1 << 20, 64)):
+        k = np.arange(n, dtype=np.float64)
+        A = tb.Toeplitz(torch.from_numpy(0.9 ** k).cuda(), torch.from_numpy(0.4 ** k).cuda())
+        FA, M = tb.factorize(A), tb.factorize(tb.strang(A))
+        B = tb.colmajor(n, l)
+        B.copy_(torch.randn(n, l, dtype=torch.float64, device="cuda"))
+        tol = 100 * 2.220446049250313e-16
+        X = tb.colmajor(n, l)
+
+        def batched():
+            X.zero_()
+            return tb.cgs_batched(FA, X, B, M, 1000, tol)
+
+        def looped(cols=8):
+            for j in range(cols):
+                tb.cgs(FA, torch.zeros(n, dtype=torch.float64, device="cuda"), B[:, j].contiguous(), M, 1000, tol)
+
+        _, errs, its, flags = batched()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); batched(); torch.cuda.synchronize(); tb_ = time.perf_counter() - t0
+        looped(2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); looped(8); torch.cuda.synchronize(); tl = (time.perf_counter() - t0) / 8
+        out(config="C6 Toeplitz{Float64} n=2^%d \\ %d right-hand sides, cgs + Strang" % (int(np.log2(n)), l),
+            batched_solves_per_s=l / tb_, column_loop_solves_per_s=1.0 / tl, iterations=[min(its), max(its)],
+            flags=sorted(set(flags)), max_rel_residual=max(errs))
+
+
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if "=" not in a]
     for kv in (a for a in sys.argv[1:] if "=" in a):       # tuning: library options, e.g. l2max_f64=13

@@ -1,0 +1,137 @@
+"""Batched cgs / cg (all columns of ldiv!(A, B::Matrix) iterating together, src/linearalgebra.jl:102-110) against the
+oracle's per-column solves (src/iterativeLinearSolvers.jl:9-215): same iterates, iteration counts and flags per column,
+including columns that converge at different iterations, zero columns (early return) and a fixed iteration budget."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import toeplitz_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tb():
+    import toeplitz_b200 as tb
+    return tb
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _devmat(a):
+    return torch.from_numpy(np.ascontiguousarray(a.T)).cuda().t()
+
+
+def _rel(a, b):
+    den = np.linalg.norm(np.asarray(b).ravel())
+    return np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel()) / (den if den > 0 else 1.0)
+
+
+def _p(base, n, dtype):
+    return (base ** np.arange(n)).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.complex64], ids=lambda d: np.dtype(d).name)
+def test_cgs_batched_matches_per_column_oracle(tb, dtype):
+    n, l = 3000, 7
+    rng = np.random.default_rng(21)
+    single = np.dtype(dtype) == np.dtype(np.complex64)
+    v = _p(0.5, n, dtype)
+    Ao, Ad = O.SymmetricToeplitz(v), tb.SymmetricToeplitz(_dev(v))
+    B = rng.standard_normal((n, l)).astype(dtype)
+    B[:, 2] = 0                                  # early return: error 0 < tol at the start
+    B[:, 4] = Ao.dense()[:, 0]                   # solved almost at once: converges well before the others
+    tol = 1e-5 if single else 100 * np.finfo(np.float64).eps
+    Mo, Md = O.factorize(O.strang(Ao)), tb.factorize(tb.strang(Ad))
+    X = tb.colmajor(n, l, _dev(B[:1]).dtype)
+    X.zero_()
+    X, errs, its, flags = tb.cgs_batched(Ad, X, _devmat(B), Md, 50, tol)
+    Xh = X.cpu().numpy()
+    seen = set()
+    for j in range(l):
+        xo, eo, ito, fo = O.cgs(Ao, np.zeros(n, dtype), B[:, j].copy(), Mo, 50, tol)
+        assert flags[j] == fo and abs(its[j] - ito) <= 1, (j, its[j], ito, flags[j], fo)
+        assert _rel(Xh[:, j], xo) <= (1e-4 if single else 1e-10), j
+        assert errs[j] <= max(10 * eo, tol)
+        seen.add(its[j])
+    assert its[2] == 0 and len(seen) >= 3        # columns really stopped at different iterations
+    # fixed budget without convergence: every column runs exactly 3 iterations and reports flag 1
+    X2 = tb.colmajor(n, l, X.dtype)
+    X2.zero_()
+    Bn = rng.standard_normal((n, l)).astype(dtype)
+    X2, errs2, its2, flags2 = tb.cgs_batched(Ad, X2, _devmat(Bn), Md, 3, 0.0)
+    for j in range(l):
+        xo, eo, ito, fo = O.cgs(Ao, np.zeros(n, dtype), Bn[:, j].copy(), Mo, 3, 0.0)
+        assert (its2[j], flags2[j]) == (ito, fo) == (3, 1)
+        assert _rel(X2[:, j].cpu().numpy(), xo) <= (1e-3 if single else 1e-9)
+
+
+def test_cg_batched_matches_per_column_oracle(tb):
+    n, l = 2500, 6
+    rng = np.random.default_rng(22)
+    v = _p(0.5, n, np.float64)
+    Ao, Ad = O.SymmetricToeplitz(v), tb.SymmetricToeplitz(_dev(v))
+    B = rng.standard_normal((n, l))
+    B[:, 1] = 0                                  # the reference's value-less early return -> flag 2
+    tol = 100 * np.finfo(np.float64).eps
+    Mo, Md = O.factorize(O.strang(Ao)), tb.factorize(tb.strang(Ad))
+    X = tb.colmajor(n, l)
+    X.zero_()
+    X, errs, its, flags = tb.cg_batched(Ad, X, _devmat(B), Md, 60, tol)
+    for j in range(l):
+        res = O.cg(Ao, np.zeros(n), B[:, j].copy(), Mo, 60, tol)
+        if res is None:
+            assert flags[j] == 2 and its[j] == 0
+            continue
+        xo, eo, ito, fo = res
+        assert flags[j] == fo and abs(its[j] - ito) <= 1
+        assert _rel(X[:, j].cpu().numpy(), xo) <= 1e-10
+    with pytest.raises(tb.ArgumentError):
+        tb.cg_batched(Ad, X.to(torch.complex128), _devmat(B.astype(np.complex128)), Md, 5, tol)
+
+
+@pytest.mark.parametrize("kind", ["toeplitz", "symmetric", "lower", "upper"])
+def test_matrix_ldiv_goes_through_the_batched_solvers(tb, kind):
+    """ldiv!(A, B::Matrix) (test/runtests.jl:58-59,103-105) with enough columns to matter, odd count, padded ld."""
+    n, l = 1500, 9
+    rng = np.random.default_rng(23)
+    if kind == "toeplitz":
+        vc, vr = _p(0.9, n, np.float64), _p(0.4, n, np.float64)
+        Ao, Ad = O.Toeplitz(vc, vr), tb.Toeplitz(_dev(vc), _dev(vr))
+    else:
+        v = _p(0.9, n, np.float64)
+        cls = {"symmetric": "SymmetricToeplitz", "lower": "LowerTriangularToeplitz", "upper": "UpperTriangularToeplitz"}[kind]
+        Ao, Ad = getattr(O, cls)(v), getattr(tb, cls)(_dev(v))
+    B = rng.standard_normal((n, l))
+    ref = np.linalg.solve(Ao.dense(), B)
+    big = torch.full((l, n + 5), float("nan"), dtype=torch.float64, device="cuda")
+    big[:, :n] = _dev(B.T.copy())
+    Bd = big.t()[:n, :]
+    l0 = tb.launch_count()
+    tb.ldiv_(Ad, Bd)
+    assert _rel(Bd.cpu().numpy(), ref) <= np.sqrt(np.finfo(float).eps)
+    assert tb.launch_count() - l0 < 60 * 40      # far fewer launches than nine separate solves
+    assert bool(torch.isnan(big[:, n:]).all())   # padding untouched
+
+
+def test_batched_chunking_and_errors(tb):
+    n, l = 1024, 11
+    rng = np.random.default_rng(24)
+    v = _p(0.5, n, np.float64)
+    Ad = tb.SymmetricToeplitz(_dev(v))
+    Md = tb.factorize(tb.strang(Ad))
+    B = rng.standard_normal((n, l))
+    tol = 100 * np.finfo(np.float64).eps
+    X1 = tb.colmajor(n, l); X1.zero_()
+    X1, e1, i1, f1 = tb.cgs_batched(Ad, X1, _devmat(B), Md, 40, tol)
+    tb.set_option("krylov_work_bytes", 8 * n * 8 * 4)        # four columns per chunk -> 3 chunks, the last one odd
+    try:
+        X2 = tb.colmajor(n, l); X2.zero_()
+        X2, e2, i2, f2 = tb.cgs_batched(Ad, X2, _devmat(B), Md, 40, tol)
+    finally:
+        tb.set_option("krylov_work_bytes", 16 << 30)
+    assert i1 == i2 and f1 == f2 and _rel(X2.cpu().numpy(), X1.cpu().numpy()) <= 1e-13
+    with pytest.raises(tb.DimensionMismatch):
+        tb.cgs_batched(Ad, tb.colmajor(n, l), _devmat(B[:, :3].copy()), Md, 5, tol)

@@ -22,6 +22,7 @@ EXPORTS = [
     "tb200_precond_vector", "tb200_levinson_batched", "tb200_durbin_batched", "tb200_cgs", "tb200_cg",
     "tb200_factorize_empty", "tb200_spectrum_buffer", "tb200_launch_count", "tb200_set_option",
     "tb200_pass_times", "tb200_trench", "tb200_tri_smallinv", "tb200_levinson_multirhs",
+    "tb200_cgs_batched", "tb200_cg_batched",
 ]
 
 
@@ -76,6 +77,8 @@ def lib() -> ctypes.CDLL:
         "tb200_durbin_batched": [ci, i64, i64, vp, i64, vp, i64, vp],
         "tb200_cgs": [vp, vp, vp, vp, ci, i64, ci, dbl, pd, pi, pi, vp],
         "tb200_cg": [vp, vp, vp, vp, ci, i64, ci, dbl, pd, pi, pi, vp],
+        "tb200_cgs_batched": [vp, vp, vp, i64, vp, i64, ci, i64, i64, ci, dbl, pd, pi, pi, vp],
+        "tb200_cg_batched": [vp, vp, vp, i64, vp, i64, ci, i64, i64, ci, dbl, pd, pi, pi, vp],
         "tb200_spectrum_buffer": [vp, pvp, pi64],
         "tb200_set_option": [ctypes.c_char_p, i64],
         "tb200_pass_times": [pd, pi64],

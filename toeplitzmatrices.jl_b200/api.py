@@ -515,9 +515,21 @@ def ldiv_(A, b: torch.Tensor) -> torch.Tensor:
         solver = lambda col: cgs(FA, torch.zeros_like(col), col, pre, 1000, tol)[0]
     else:
         raise TypeError(type(A))
-    cols = [b] if b.dim() == 1 else [b[:, j] for j in range(b.shape[1])]
-    for col in cols:
-        col.copy_(solver(col.contiguous()))
+    if b.dim() == 1:
+        b.copy_(solver(b.contiguous()))
+        return b
+    # matrix right-hand side (:102-110): the reference loops over the columns; here they iterate together
+    Bc = b if _is_colmajor(b) else to_colmajor(b)
+    Xs = colmajor(Bc.shape[0], Bc.shape[1], Bc.dtype, Bc.device)
+    Xs.zero_()
+    if isinstance(A, SymmetricToeplitz):
+        _, _, _, flags = cg_batched(FA, Xs, Bc, pre, 1000, tol)
+        if any(f == 2 for f in flags):
+            raise ToeplitzB200Error("MethodError: cg returned nothing (initial residual below tol, "
+                                    "src/iterativeLinearSolvers.jl:57-59)")
+    else:
+        cgs_batched(FA, Xs, Bc, pre, 1000, tol)
+    b.copy_(Xs)
     return b
 
 
@@ -751,6 +763,39 @@ def cg(A, x, b, M, max_it, tol):
     if res[3] == 2:
         return None
     return res
+
+
+def _krylov_batched(fn, A, X, B, M, max_it, tol):
+    FA = A if isinstance(A, ToeplitzFactorization) else factorize(A)
+    Mh = None if M is None else _circ_fact(M)._h
+    if X.dtype != B.dtype:
+        raise ArgumentError("MethodError: X and B must have the same element type")
+    if X.dim() != 2 or B.dim() != 2 or X.shape != B.shape:
+        raise DimensionMismatch("X and B must be matrices of the same size")
+    if not _is_colmajor(X) or not _is_colmajor(B):
+        raise ArgumentError("X and B must be column-major (tb.colmajor / tb.to_colmajor)")
+    if _with_prec(B.dtype, FA.dtype) != B.dtype:
+        raise ArgumentError("vector precision must match the matrix precision")
+    l = B.shape[1]
+    err = (ctypes.c_double * max(l, 1))()
+    it = (ctypes.c_int * max(l, 1))()
+    flag = (ctypes.c_int * max(l, 1))()
+    check(fn(FA._h, Mh, X.data_ptr(), _ld(X), B.data_ptr(), _ld(B), _DT[B.dtype], B.shape[0], l, int(max_it), float(tol),
+             err, it, flag, _stream()))
+    return X, list(err)[:l], list(it)[:l], list(flag)[:l]
+
+
+def cgs_batched(A, X, B, M, max_it, tol):
+    """All columns of ``B`` through ``cgs`` at once (the column loop of ``ldiv!(A, B::Matrix)``, src/linearalgebra.jl:
+    102-110): ``(X, errors, iters, flags)`` with one entry per column."""
+    return _krylov_batched(L.lib().tb200_cgs_batched, A, X, B, M, max_it, tol)
+
+
+def cg_batched(A, X, B, M, max_it, tol):
+    """All columns of ``B`` through ``cg`` at once; ``flags[j] == 2`` marks the reference's value-less early return."""
+    if not _is_real(B.dtype):
+        raise ArgumentError("MethodError: cg is defined for BlasReal element types")
+    return _krylov_batched(L.lib().tb200_cg_batched, A, X, B, M, max_it, tol)
 
 
 # ------------------------------------------------------------------------------------

@@ -19,6 +19,7 @@
 #include "pipe_kernels.cuh"
 #include "aux_kernels.cuh"
 #include "blas1.cuh"
+#include "krylov_batched.cuh"
 
 namespace tb {
 
@@ -29,6 +30,7 @@ static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static std::atomic<long long> g_group_bytes{48ll << 20};   // two-level scratch budget per group
 static std::atomic<long long> g_host_chunk_bytes{256ll << 20};
+static std::atomic<long long> g_krylov_work_bytes{16ll << 30};   // work-vector budget of the batched cgs / cg (columns per chunk)
 static std::atomic<int> g_time_passes{0};
 static std::atomic<int> g_overlap_streams{2};   // helper streams for group overlap (0/1 = off)
 static std::atomic<int> g_mega{0};               // opt-in persistent single-launch path (measured slower than 3 kernels x 2 streams)
@@ -704,6 +706,7 @@ int tb200_debug_set_trace(void* p) { return cuda_status(tb::debug_set_trace((lon
 int tb200_set_option(const char* name, int64_t value) {
     if (!name) return set_error(TB200_BAD_ARG, "option name is NULL");
     if (!strcmp(name, "group_bytes")) { g_group_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
+    if (!strcmp(name, "krylov_work_bytes")) { g_krylov_work_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "host_chunk_bytes")) { g_host_chunk_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "time_passes")) { g_time_passes = value ? 1 : 0; return TB200_OK; }
     if (!strcmp(name, "overlap_streams")) { g_overlap_streams = (int)std::min<int64_t>(std::max<int64_t>(value, 0), tb200_fact::MAXS); return TB200_OK; }
@@ -1313,9 +1316,156 @@ static int cg_t(tb200_fact* A, tb200_fact* M, T* x, const T* b, int dtype, int64
     return TB200_OK;
 }
 
+
+// ---- batched cgs / cg over the columns of B (krylov_batched.cuh) ---------------------------------------------
+template <typename T>
+static int krylov_batched_t(bool is_cg, tb200_fact* A, tb200_fact* M, T* X, int64_t ldx, const T* B, int64_t ldb, int dtype,
+                            int64_t n, int64_t nrhs, int max_it, double tol, double* err, int* iter, int* flag, cudaStream_t s) {
+    const int nvec = is_cg ? 4 : 8;
+    int64_t chunk = std::max<int64_t>(1, g_krylov_work_bytes.load() / (int64_t)(sizeof(T) * (size_t)n * nvec));
+    chunk = std::min<int64_t>(std::min<int64_t>(chunk, nrhs), 65535);
+    if (chunk > 1 && (chunk & 1)) --chunk;                       // keep real columns paired in the transforms
+    std::shared_ptr<DevBuf> work, stbuf, partials, counters, nact;
+    TB_TRY(dev_alloc(work, sizeof(T) * (size_t)n * (size_t)chunk * nvec, "batched Krylov work vectors"));
+    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>(128, (n + 2047) / 2048));
+    TB_TRY(dev_alloc(stbuf, sizeof(KState) * (size_t)chunk, "Krylov state"));
+    TB_TRY(dev_alloc(partials, sizeof(double) * 4 * gx * (size_t)chunk, "dot partials"));
+    TB_TRY(dev_alloc(counters, sizeof(unsigned) * (size_t)chunk, "dot counters"));
+    TB_TRY(dev_alloc(nact, sizeof(int), "active counter"));
+    KState* st = (KState*)stbuf->p;
+    std::vector<KState> host_st((size_t)chunk);
+    const double one[2] = {1, 0}, zero[2] = {0, 0}, minus[2] = {-1, 0};
+    const size_t vsz = (size_t)n * (size_t)chunk;
+    T* w = (T*)work->p;
+    for (int64_t c0 = 0; c0 < nrhs; c0 += chunk) {
+        const int64_t c = std::min(chunk, nrhs - c0);
+        T* Xc = X + c0 * ldx;
+        const T* Bc = B + c0 * ldb;
+        const dim3 gdot(gx, (unsigned)c), gew((unsigned)std::max<long long>(1, std::min<long long>((n + 1023) / 1024, 2048)), (unsigned)c);
+        const unsigned gs = (unsigned)((c + 127) / 128);
+        int h_active = 0;
+        auto dots = [&](const T* a1, const T* b1, long long ld1, const T* a2, const T* b2, int only_active) -> int {
+            k_bdot2<T><<<gdot, 256, 0, s>>>(a1, b1, ld1, a2, b2, n, n, (double*)partials->p, (unsigned*)counters->p, st, only_active);
+            count_launch();
+            return cuda_status(cudaGetLastError(), "k_bdot2");
+        };
+        auto step = [&](int which, int it, bool count) -> int {
+            if (count) TB_CUDA(cudaMemsetAsync(nact->p, 0, sizeof(int), s), "memset");
+            k_kstep<<<gs, 128, 0, s>>>(st, (int)c, which, it, max_it, tol, (int*)nact->p);
+            count_launch();
+            TB_CUDA(cudaGetLastError(), "k_kstep");
+            if (count) {
+                TB_CUDA(cudaMemcpyAsync(&h_active, nact->p, sizeof(int), cudaMemcpyDeviceToHost, s), "active readback");
+                TB_CUDA(cudaStreamSynchronize(s), "Krylov sync");
+            }
+            return TB200_OK;
+        };
+        auto mulA = [&](T* y, const T* x, int64_t ldxx, const double* a, const double* b) -> int {
+            return tb200_mul(A, y, n, dtype, x, ldxx, dtype, c, a, b, (void*)s);
+        };
+        auto precond = [&](T* out_v, const T* in_v) -> int {
+            if (!M) {
+                if (out_v != in_v) TB_CUDA(cudaMemcpyAsync(out_v, in_v, sizeof(T) * (size_t)n * (size_t)c, cudaMemcpyDeviceToDevice, s), "copy");
+                return TB200_OK;
+            }
+            return tb200_circ_ldiv(M, out_v, n, in_v, n, dtype, c, (void*)s);
+        };
+        TB_CUDA(cudaMemsetAsync(counters->p, 0, sizeof(unsigned) * (size_t)c, s), "memset");
+        TB_CUDA(cudaMemsetAsync(work->p, 0, sizeof(T) * vsz * nvec, s), "memset");          // :141-146 zeros
+        TB_TRY(dots(Bc, Bc, ldb, nullptr, nullptr, 0));
+        TB_TRY(step(KS_BNRM, 0, false));
+        if (!is_cg) {
+            T* u = w; T* p = u + vsz; T* ph = p + vsz; T* q = ph + vsz; T* uh = q + vsz; T* vh = uh + vsz; T* r = vh + vsz; T* rt = r + vsz;
+            TB_CUDA(cudaMemcpy2DAsync(r, sizeof(T) * (size_t)n, Bc, sizeof(T) * (size_t)ldb, sizeof(T) * (size_t)n, (size_t)c,
+                                      cudaMemcpyDeviceToDevice, s), "copy");                   // :149
+            TB_TRY(mulA(r, Xc, ldx, minus, one));                                              // :150
+            TB_TRY(dots(r, r, n, nullptr, nullptr, 0));
+            TB_TRY(step(KS_INIT_CGS, 0, true));
+            if (h_active > 0) {
+                TB_CUDA(cudaMemcpyAsync(rt, r, sizeof(T) * (size_t)n * (size_t)c, cudaMemcpyDeviceToDevice, s), "copy");   // :158
+                TB_TRY(dots(rt, r, n, nullptr, nullptr, 1));
+                TB_TRY(step(KS_RHO0, 0, false));
+                for (int it = 1; it <= max_it && h_active > 0; ++it) {
+                    TB_TRY(step(KS_CGS_BEGIN, it, false));
+                    k_bcgs_dir<T><<<gew, 256, 0, s>>>(u, p, r, q, st, it == 1, n, n);          // :168-177
+                    count_launch();
+                    TB_TRY(precond(ph, p));                                                    // :179-180
+                    TB_TRY(mulA(vh, ph, n, one, zero));                                        // :182
+                    TB_TRY(dots(rt, vh, n, nullptr, nullptr, 1));
+                    TB_TRY(step(KS_CGS_ALPHA, it, false));                                     // :184
+                    k_bcgs_q<T><<<gew, 256, 0, s>>>(q, uh, u, vh, st, n, n);                   // :185-188
+                    count_launch();
+                    TB_TRY(precond(uh, uh));                                                   // :189
+                    TB_TRY(mulA(vh, uh, n, one, zero));                                        // A*uh (vh is free again)
+                    k_bxr<T><<<gew, 256, 0, s>>>(Xc, ldx, r, uh, vh, st, n, n);                // :192-196
+                    count_launch();
+                    TB_TRY(dots(r, r, n, rt, r, 1));
+                    TB_TRY(step(KS_CGS_END, it, true));                                        // :198-201
+                }
+            }
+        } else {
+            T* z = w; T* q = z + vsz; T* p = q + vsz; T* r = p + vsz;
+            TB_CUDA(cudaMemcpy2DAsync(r, sizeof(T) * (size_t)n, Bc, sizeof(T) * (size_t)ldb, sizeof(T) * (size_t)n, (size_t)c,
+                                      cudaMemcpyDeviceToDevice, s), "copy");
+            TB_TRY(mulA(r, Xc, ldx, minus, one));                                              // :55
+            TB_TRY(dots(r, r, n, nullptr, nullptr, 0));
+            TB_TRY(step(KS_INIT_CG, 0, true));
+            for (int it = 1; it <= max_it && h_active > 0; ++it) {
+                TB_TRY(precond(z, r));                                                         // :64-65
+                TB_TRY(dots(r, z, n, nullptr, nullptr, 1));
+                TB_TRY(step(KS_CG_BEGIN, it, false));                                          // :67-68
+                k_bcg_dir<T><<<gew, 256, 0, s>>>(p, z, st, it == 1, n, n);                     // :69-76
+                count_launch();
+                TB_TRY(mulA(q, p, n, one, zero));                                              // :79
+                TB_TRY(dots(p, q, n, nullptr, nullptr, 1));
+                TB_TRY(step(KS_CG_ALPHA, it, false));                                          // :80
+                k_bxr<T><<<gew, 256, 0, s>>>(Xc, ldx, r, p, q, st, n, n);                      // :81-84
+                count_launch();
+                TB_TRY(dots(r, r, n, nullptr, nullptr, 1));
+                TB_TRY(step(KS_CG_END, it, true));                                             // :86-88
+            }
+        }
+        TB_CUDA(cudaGetLastError(), "batched Krylov kernels");
+        TB_CUDA(cudaMemcpyAsync(host_st.data(), st, sizeof(KState) * (size_t)c, cudaMemcpyDeviceToHost, s), "state readback");
+        TB_CUDA(cudaStreamSynchronize(s), "Krylov sync");
+        for (int64_t j = 0; j < c; ++j) {
+            if (err) err[c0 + j] = host_st[(size_t)j].error;
+            if (iter) iter[c0 + j] = host_st[(size_t)j].iter;
+            if (flag) flag[c0 + j] = host_st[(size_t)j].flag;
+        }
+    }
+    return TB200_OK;
+}
+
+static int krylov_batched(bool is_cg, tb200_fact* A, tb200_fact* M, void* X, int64_t ldx, const void* B, int64_t ldb, int dtype,
+                          int64_t n, int64_t nrhs, int max_it, double tol, double* err, int* iter, int* flag, void* stream) {
+    DeviceGuard dev_guard(A);
+    if (nrhs < 0) return set_error(TB200_BAD_ARG, "negative column count");
+    TB_TRY(check_krylov(A, M, dtype, n, X, B));
+    if (ldx < n || ldb < n) return set_error(TB200_DIM_MISMATCH, "leading dimensions must be at least n = %lld", (long long)n);
+    if (is_cg && dt_is_cplx(dtype)) return set_error(TB200_BAD_ARG, "cg is defined for real (BlasReal) element types only");
+    if (nrhs == 0) return TB200_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (dtype) {
+    case TB200_F32: return krylov_batched_t<float>(is_cg, A, M, (float*)X, ldx, (const float*)B, ldb, dtype, n, nrhs, max_it, tol, err, iter, flag, s);
+    case TB200_F64: return krylov_batched_t<double>(is_cg, A, M, (double*)X, ldx, (const double*)B, ldb, dtype, n, nrhs, max_it, tol, err, iter, flag, s);
+    case TB200_C32: return krylov_batched_t<float2>(is_cg, A, M, (float2*)X, ldx, (const float2*)B, ldb, dtype, n, nrhs, max_it, tol, err, iter, flag, s);
+    default: return krylov_batched_t<double2>(is_cg, A, M, (double2*)X, ldx, (const double2*)B, ldb, dtype, n, nrhs, max_it, tol, err, iter, flag, s);
+    }
+}
+
 }  // namespace tb
 
 extern "C" {
+
+int tb200_cgs_batched(tb200_handle_t A, tb200_handle_t M, void* X, int64_t ldx, const void* B, int64_t ldb, int dtype, int64_t n,
+                      int64_t nrhs, int max_it, double tol, double* err, int* iter, int* flag, void* stream) {
+    return krylov_batched(false, A, M, X, ldx, B, ldb, dtype, n, nrhs, max_it, tol, err, iter, flag, stream);
+}
+int tb200_cg_batched(tb200_handle_t A, tb200_handle_t M, void* X, int64_t ldx, const void* B, int64_t ldb, int dtype, int64_t n,
+                     int64_t nrhs, int max_it, double tol, double* err, int* iter, int* flag, void* stream) {
+    return krylov_batched(true, A, M, X, ldx, B, ldb, dtype, n, nrhs, max_it, tol, err, iter, flag, stream);
+}
 
 int tb200_cgs(tb200_handle_t A, tb200_handle_t M, void* x, const void* b, int dtype, int64_t n, int max_it, double tol,
               double* err, int* iter, int* flag, void* stream) {

@@ -1,0 +1,195 @@
+// Batched Krylov solvers: the reference's matrix `ldiv!` is a serial column loop over single-vector cgs / cg
+// solves (/root/reference/src/linearalgebra.jl:102-110 calling :133-136, :152, :399-402).  Here all columns of a chunk
+// iterate together: the structured products and preconditioner solves run on the batched FFT path (two real columns
+// per transform), the vector updates are single sweeps over the whole chunk, and every per-column scalar
+// (rho, alpha, beta, error, flags) lives on the device -- one host synchronisation per iteration (the number of
+// columns still iterating) instead of two per column.  Per column the arithmetic is the reference's
+// (/root/reference/src/iterativeLinearSolvers.jl:99-215 cgs, :9-97 cg): a column that converges, breaks down or
+// returns early is frozen with its own (error, iter, flag) while the others go on.
+#pragma once
+#include "blas1.cuh"
+
+namespace tb {
+
+struct KState {
+    double rho[2], rho1[2], rhon[2], alpha[2], beta[2], dot[4];
+    double bnrm2, error;
+    int iter, flag, active, pad;
+};
+
+__device__ __forceinline__ double2 zdiv(const double* a, const double* b) {
+    const double d = b[0] * b[0] + b[1] * b[1];
+    return make_double2((a[0] * b[0] + a[1] * b[1]) / d, (a[1] * b[0] - a[0] * b[1]) / d);
+}
+
+// dot[0..1] = dot(a1_j, b1_j), dot[2..3] = dot(a2_j, b2_j) for every column j = blockIdx.y (all four matrices share the
+// leading dimension ld unless ld1 is given for the first pair).  Deterministic: per-CTA partials, the last CTA of a
+// column sums them in index order.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_bdot2(const T* __restrict__ a1, const T* __restrict__ b1, long long ld1, const T* __restrict__ a2, const T* __restrict__ b2,
+        long long ld2, long long n, double* __restrict__ partials, unsigned* __restrict__ counters, KState* __restrict__ st,
+        int only_active) {
+    const int j = blockIdx.y;
+    if (only_active && !st[j].active) return;
+    const T* pa1 = a1 + j * ld1; const T* pb1 = b1 + j * ld1;
+    const T* pa2 = a2 ? a2 + j * ld2 : nullptr; const T* pb2 = b2 ? b2 + j * ld2 : nullptr;
+    double acc[4] = {0, 0, 0, 0};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        dot_acc(pa1[i], pb1[i], acc[0], acc[1]);
+        if (pa2) dot_acc(pa2[i], pb2[i], acc[2], acc[3]);
+    }
+    __shared__ double red[4][8];
+    __shared__ bool is_last;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], o);
+        if ((threadIdx.x & 31) == 0) red[v][threadIdx.x >> 5] = acc[v];
+    }
+    __syncthreads();
+    double* mine = partials + ((size_t)j * gridDim.x) * 4;
+    if (threadIdx.x == 0) {
+        for (int v = 0; v < 4; ++v) {
+            double s = 0;
+            for (int w = 0; w < 8; ++w) s += red[v][w];
+            mine[(size_t)blockIdx.x * 4 + v] = s;
+        }
+        __threadfence();
+        const unsigned done = atomicAdd(counters + j, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < 4) {
+        double s = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&mine[(size_t)b * 4 + threadIdx.x]);
+        st[j].dot[threadIdx.x] = s;
+        if (threadIdx.x == 0) counters[j] = 0;
+    }
+}
+
+// ---- per-column scalar steps (one thread per column) ---------------------------------------------------------
+enum KStep : int { KS_BNRM = 0, KS_INIT_CGS, KS_INIT_CG, KS_RHO0, KS_CGS_BEGIN, KS_CGS_ALPHA, KS_CGS_END, KS_CG_BEGIN, KS_CG_ALPHA, KS_CG_END };
+
+__global__ void k_kstep(KState* __restrict__ st, int ncols, int step, int it, int max_it, double tol, int* __restrict__ nactive) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    KState& s = st[j];
+    switch (step) {
+    case KS_BNRM:                                   // :136 / :44-47
+        s.bnrm2 = sqrt(s.dot[0]);
+        if (s.bnrm2 == 0.0) s.bnrm2 = 1.0;
+        s.iter = 0; s.flag = 0; s.active = 1;
+        s.rho[0] = s.rho[1] = s.rho1[0] = s.rho1[1] = 0.0;
+        break;
+    case KS_INIT_CGS:                               // :152-156
+    case KS_INIT_CG:                                // :55-59 (flag 2 = the reference's value-less early return)
+        s.error = sqrt(s.dot[0]) / s.bnrm2;
+        if (s.error < tol) { s.active = 0; s.flag = (step == KS_INIT_CG) ? 2 : 0; }
+        if (s.active) atomicAdd(nactive, 1);
+        break;
+    case KS_RHO0:
+        s.rhon[0] = s.dot[0]; s.rhon[1] = s.dot[1];
+        break;
+    case KS_CGS_BEGIN:                              // :163-169
+        if (!s.active) break;
+        s.iter = it;
+        s.rho[0] = s.rhon[0]; s.rho[1] = s.rhon[1];
+        if (s.rho[0] == 0.0 && s.rho[1] == 0.0) { s.active = 0; s.flag = (s.error <= tol) ? 0 : -1; break; }
+        if (it > 1) { const double2 b = zdiv(s.rho, s.rho1); s.beta[0] = b.x; s.beta[1] = b.y; }
+        else { s.beta[0] = s.beta[1] = 0.0; }
+        break;
+    case KS_CGS_ALPHA:                              // :184
+    case KS_CG_ALPHA: {                             // :80
+        if (!s.active) break;
+        const double2 a = zdiv(s.rho, s.dot);
+        s.alpha[0] = a.x; s.alpha[1] = a.y;
+        break;
+    }
+    case KS_CGS_END:                                // :198-203, flag logic :205-213
+        if (!s.active) break;
+        s.error = sqrt(s.dot[0]) / s.bnrm2;
+        s.rhon[0] = s.dot[2]; s.rhon[1] = s.dot[3];
+        if (s.error <= tol) { s.active = 0; s.flag = 0; }
+        else {
+            s.rho1[0] = s.rho[0]; s.rho1[1] = s.rho[1];
+            if (it == max_it) { s.active = 0; s.flag = 1; }
+        }
+        if (s.active) atomicAdd(nactive, 1);
+        break;
+    case KS_CG_BEGIN:                               // :67-68
+        if (!s.active) break;
+        s.iter = it;
+        s.rho[0] = s.dot[0]; s.rho[1] = s.dot[1];
+        if (it > 1) { const double2 b = zdiv(s.rho, s.rho1); s.beta[0] = b.x; s.beta[1] = b.y; }
+        else { s.beta[0] = s.beta[1] = 0.0; }
+        break;
+    case KS_CG_END:                                 // :86-91
+        if (!s.active) break;
+        s.error = sqrt(s.dot[0]) / s.bnrm2;
+        if (s.error <= tol) { s.active = 0; s.flag = 0; }
+        else {
+            s.rho1[0] = s.rho[0]; s.rho1[1] = s.rho[1];
+            if (it == max_it) { s.active = 0; s.flag = 1; }
+        }
+        if (s.active) atomicAdd(nactive, 1);
+        break;
+    }
+}
+
+// ---- vector sweeps over a chunk: grid (x over n, y = column); frozen columns are skipped ---------------------------
+#define TB_KCOL_LOOP(nn)                                                                                         \
+    const int j = blockIdx.y;                                                                                    \
+    if (!st[j].active) return;                                                                                   \
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (nn); i += (long long)gridDim.x * blockDim.x)
+
+// cgs :168-177
+template <typename T>
+__global__ void k_bcgs_dir(T* __restrict__ u, T* __restrict__ p, const T* __restrict__ r, const T* __restrict__ q,
+                           const KState* __restrict__ st, int first, long long n, long long ld) {
+    const double2 beta = make_double2(st[blockIdx.y].beta[0], st[blockIdx.y].beta[1]);
+    const long long o = blockIdx.y * ld;
+    TB_KCOL_LOOP(n) {
+        if (first) { const T rv = r[o + i]; u[o + i] = rv; p[o + i] = rv; }
+        else {
+            const T qv = q[o + i];
+            const T uv = v_add(r[o + i], s_mul<T>(beta, qv));
+            u[o + i] = uv;
+            p[o + i] = v_add(uv, s_mul<T>(beta, v_add(qv, s_mul<T>(beta, p[o + i]))));
+        }
+    }
+}
+// cgs :185-188
+template <typename T>
+__global__ void k_bcgs_q(T* __restrict__ q, T* __restrict__ uh, const T* __restrict__ u, const T* __restrict__ vh,
+                         const KState* __restrict__ st, long long n, long long ld) {
+    const double2 alpha = make_double2(st[blockIdx.y].alpha[0], st[blockIdx.y].alpha[1]);
+    const long long o = blockIdx.y * ld;
+    TB_KCOL_LOOP(n) {
+        const T uv = u[o + i];
+        const T qv = v_sub(uv, s_mul<T>(alpha, vh[o + i]));
+        q[o + i] = qv;
+        uh[o + i] = v_add(uv, qv);
+    }
+}
+// cgs :192-196 and cg :81-84:  x += alpha*d ; r -= alpha*Ad
+template <typename T>
+__global__ void k_bxr(T* __restrict__ x, long long ldx, T* __restrict__ r, const T* __restrict__ d, const T* __restrict__ Ad,
+                      const KState* __restrict__ st, long long n, long long ld) {
+    const double2 alpha = make_double2(st[blockIdx.y].alpha[0], st[blockIdx.y].alpha[1]);
+    const long long o = blockIdx.y * ld, ox = blockIdx.y * ldx;
+    TB_KCOL_LOOP(n) {
+        x[ox + i] = v_add(x[ox + i], s_mul<T>(alpha, d[o + i]));
+        r[o + i] = v_sub(r[o + i], s_mul<T>(alpha, Ad[o + i]));
+    }
+}
+// cg :69-76
+template <typename T>
+__global__ void k_bcg_dir(T* __restrict__ p, const T* __restrict__ z, const KState* __restrict__ st, int first, long long n,
+                          long long ld) {
+    const double2 beta = make_double2(st[blockIdx.y].beta[0], st[blockIdx.y].beta[1]);
+    const long long o = blockIdx.y * ld;
+    TB_KCOL_LOOP(n) { p[o + i] = first ? z[o + i] : v_add(z[o + i], s_mul<T>(beta, p[o + i])); }
+}
+
+}  // namespace tb
