@@ -114,6 +114,22 @@ def c4m():
         replicated_solves_per_s=nrhs / t2)
 
 
+def c4s():
+    """Levinson / Durbin at smaller orders (same kernels as C4)"""
+    for n in (32, 64, 128, 256, 768, 1024, 2048):
+        nsys = 1 << 20 if n <= 256 else 1 << 17
+        R = (torch.rand((nsys, n), dtype=torch.float64, device="cuda") / n).t()
+        B = torch.randn((nsys, n), dtype=torch.float64, device="cuda").t()
+        X = tb.colmajor(n, nsys)
+        Rl = R[: n - 1, :]
+        t = timed(lambda: tb.levinson_(X, Rl, B), 3, warm=1)
+        Y = tb.colmajor(n, nsys)
+        td = timed(lambda: tb.durbin_(Y, R), 3, warm=1)
+        out(config="C4s n=%d x %d systems" % (n, nsys), levinson_solves_per_s=nsys / t, durbin_solves_per_s=nsys / td,
+            levinson_tflops=4.0 * n * n * nsys / t / 1e12, durbin_tflops=2.0 * n * n * nsys / td / 1e12,
+            levinson_alg_gbs=nsys * (3 * n * 8) / t / 1e9)
+
+
 def c6():
     """Toeplitz \\ B with many right-hand sides: batched cgs + Strang vs the reference's column loop of single solves."""
     for n, l in ((1 << 16, 256), (1 << 20, 64)):
