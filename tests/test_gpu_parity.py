@@ -241,7 +241,8 @@ def test_pinv_singular(tb):
             assert rel(host(tb.pinv(tb.Circulant(dev(v)), 1e-10).vc), O.circ_pinv(O.Circulant(v), 1e-10).vc) <= 1e-12
 
 
-@pytest.mark.parametrize("n", [1, 2, 8, 64, 129, 200, 384, 512, 513, 700, 768, 769, 1024, 1025, 1536, 1537, 2048, 2100])
+@pytest.mark.parametrize("n", [1, 2, 8, 16, 17, 32, 33, 48, 49, 64, 65, 96, 97, 128, 129, 192, 193, 200, 256, 257, 384, 512, 513,
+                               700, 768, 769, 1024, 1025, 1536, 1537, 2048, 2100])
 def test_levinson_durbin_batched(tb, n):
     """src/directLinearSolvers.jl:15-28,100-134 batched over columns, vs the C oracle."""
     rng = np.random.default_rng(n)

@@ -458,7 +458,7 @@ template <typename R, bool DURBIN>
 static int launch_levinson(int64_t n, int64_t nsys, const R* r, int64_t ldr, const R* b, int64_t ldb, R* x,
                            int64_t ldx, const R* diag, cudaStream_t s) {
     if (nsys <= 0 || n <= 0) return TB200_OK;
-    if (n <= 2 * 16 * LB) {                   // small orders: 4 (n <= 32) or 2 (n <= 128) systems per warp
+    if (n <= 4 * 16 * LB) {                   // small orders: 8 (n <= 64), 4 (n <= 128) or 2 (n <= 256) systems per warp
         const int wpc = 4;
 #define TB_LEV_SMALL(SV, PV)                                                                                        \
     {                                                                                                               \
@@ -466,9 +466,16 @@ static int launch_levinson(int64_t n, int64_t nsys, const R* r, int64_t ldr, con
         const size_t smem = (size_t)wpc * (32 / PV) * 2 * SV * (PV * LB) * sizeof(R);                               \
         k_levinson_warp<R, SV, DURBIN, PV><<<grid, wpc * 32, smem, s>>>(n, nsys, r, ldr, b, ldb, x, ldx, diag);    \
     }
-        if (n <= 8 * LB) TB_LEV_SMALL(1, 8)
-        else if (n <= 16 * LB) TB_LEV_SMALL(1, 16)
-        else TB_LEV_SMALL(2, 16)
+        // smallest group of lanes that still holds a system in S <= 4 register blocks per lane
+        if (n <= 16) TB_LEV_SMALL(1, 4)
+        else if (n <= 32) TB_LEV_SMALL(2, 4)
+        else if (n <= 48) TB_LEV_SMALL(3, 4)
+        else if (n <= 64) TB_LEV_SMALL(4, 4)
+        else if (n <= 128 && !DURBIN) TB_LEV_SMALL(2, 16)      // measured: Levinson 102 M (16 lanes) vs 93 M (8 lanes) at n = 128
+        else if (n <= 96) TB_LEV_SMALL(3, 8)
+        else if (n <= 128) TB_LEV_SMALL(4, 8)
+        else if (n <= 192) TB_LEV_SMALL(3, 16)
+        else TB_LEV_SMALL(4, 16)
 #undef TB_LEV_SMALL
         count_launch();
         return cuda_status(cudaGetLastError(), "levinson warp kernel (several systems per warp)");
