@@ -135,3 +135,10 @@ def test_batched_chunking_and_errors(tb):
     assert i1 == i2 and f1 == f2 and _rel(X2.cpu().numpy(), X1.cpu().numpy()) <= 1e-13
     with pytest.raises(tb.DimensionMismatch):
         tb.cgs_batched(Ad, tb.colmajor(n, l), _devmat(B[:, :3].copy()), Md, 5, tol)
+    # an empty iteration budget: the reference falls through its flag logic with rho == 0 (cgs: -1) / error > tol (cg: 1)
+    X0 = tb.colmajor(n, l); X0.zero_()
+    _, e0, i0, f0 = tb.cgs_batched(Ad, X0, _devmat(B), Md, 0, tol)
+    xo, eo, ito, fo = O.cgs(O.SymmetricToeplitz(v), np.zeros(n), B[:, 0].copy(), O.factorize(O.strang(O.SymmetricToeplitz(v))), 0, tol)
+    assert set(f0) == {fo} == {-1} and set(i0) == {ito} == {0} and abs(e0[0] - eo) <= 1e-12
+    _, _, i0, f0 = tb.cg_batched(Ad, X0, _devmat(B), Md, 0, tol)
+    assert set(f0) == {1} and set(i0) == {0}

@@ -86,6 +86,7 @@ __global__ void k_kstep(KState* __restrict__ st, int ncols, int step, int it, in
     case KS_INIT_CG:                                // :55-59 (flag 2 = the reference's value-less early return)
         s.error = sqrt(s.dot[0]) / s.bnrm2;
         if (s.error < tol) { s.active = 0; s.flag = (step == KS_INIT_CG) ? 2 : 0; }
+        else if (max_it <= 0) { s.active = 0; s.flag = (step == KS_INIT_CG) ? 1 : -1; }    // empty loop: :205-213 with rho == 0 / :93-95
         if (s.active) atomicAdd(nactive, 1);
         break;
     case KS_RHO0:
