@@ -130,6 +130,23 @@ def c4s():
             levinson_alg_gbs=nsys * (3 * n * 8) / t / 1e9)
 
 
+def sweep():
+    """Batched Toeplitz{Float64} matvec across sizes: algorithmic GB/s (read x + write y) at ~512 MiB per operand."""
+    for ln in range(8, 24):
+        n = 1 << ln
+        cols = max(2, min(1 << 20, (512 << 20) // (8 * n)))
+        k = np.arange(n, dtype=np.float64)
+        A = tb.Toeplitz(torch.from_numpy(0.9 ** k).cuda(), torch.from_numpy(0.4 ** k).cuda())
+        F = tb.factorize(A)
+        X = tb.colmajor(n, cols); X.copy_(torch.randn(n, cols, dtype=torch.float64, device="cuda"))
+        Y = tb.colmajor(n, cols)
+        t = timed(lambda: tb.mul_(Y, F, X), 5)
+        info = {}
+        out(config="sweep Toeplitz{Float64} n=2^%d x %d columns" % (ln, cols), matvecs_per_s=cols / t, alg_gbs=2 * 8 * n * cols / t / 1e9,
+            frac_hbm=2 * 8 * n * cols / t / 1e9 / HBM)
+        del X, Y, F
+
+
 def c6():
     """Toeplitz \\ B with many right-hand sides: batched cgs + Strang vs the reference's column loop of single solves."""
     for n, l in ((1 << 16, 256), (1 << 20, 64)):
