@@ -132,7 +132,7 @@ def c4s():
 
 def sweep():
     """Batched Toeplitz{Float64} matvec across sizes: algorithmic GB/s (read x + write y) at ~512 MiB per operand."""
-    for ln in range(8, 24):
+    for ln in range(int(os.environ.get("SWEEP_LO", 8)), int(os.environ.get("SWEEP_HI", 24))):
         n = 1 << ln
         cols = max(2, min(1 << 20, (512 << 20) // (8 * n)))
         k = np.arange(n, dtype=np.float64)

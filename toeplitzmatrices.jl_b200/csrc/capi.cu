@@ -35,7 +35,8 @@ static std::atomic<int> g_time_passes{0};
 static std::atomic<int> g_overlap_streams{2};   // helper streams for group overlap (0/1 = off)
 static std::atomic<int> g_mega{0};               // opt-in persistent single-launch path (measured slower than 3 kernels x 2 streams)
 static std::atomic<int> g_pipe_b{0};             // opt-in cp.async double-buffered persistent pass B (measured slower)
-static std::atomic<int> g_l2max_f64{12}, g_l2max_f32{13}, g_ta_cap{0}, g_force_l1{0};   // plan tuning knobs
+static std::atomic<int> g_l2max_f64{12}, g_l2max_f32{13}, g_ta_cap{0}, g_force_l1{0};
+static std::atomic<int> g_single_max_f64{13}, g_single_max_f32{13};   // longest embedding done as ONE shared-memory transform (2^k)   // plan tuning knobs
 
 // optional per-pass device timing (bench.py's roofline leg): CUDA events recorded on the
 // launching stream around every pass while "time_passes" is on.
@@ -257,7 +258,7 @@ static int next_log2(int64_t v) { int l = 0; while ((1ll << l) < v) ++l; return 
 
 static int make_plan(tb200_fact* h) {
     const int l = h->log2np;
-    const int max_single = h->prec ? 12 : 13;
+    const int max_single = h->prec ? g_single_max_f64.load() : g_single_max_f32.load();
     if (l < 4) return set_error(TB200_UNSUPPORTED, "embedding shorter than 16 is handled by tb200_mul_direct");
     if (l <= max_single) {
         h->two_level = 0; h->log2l1 = 0; h->log2l2 = l; h->ta = 0;
@@ -706,6 +707,8 @@ int tb200_debug_set_trace(void* p) { return cuda_status(tb::debug_set_trace((lon
 int tb200_set_option(const char* name, int64_t value) {
     if (!name) return set_error(TB200_BAD_ARG, "option name is NULL");
     if (!strcmp(name, "group_bytes")) { g_group_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
+    if (!strcmp(name, "single_max_f64")) { g_single_max_f64 = (int)std::min<int64_t>(std::max<int64_t>(value, 4), 13); return TB200_OK; }
+    if (!strcmp(name, "single_max_f32")) { g_single_max_f32 = (int)std::min<int64_t>(std::max<int64_t>(value, 4), 14); return TB200_OK; }
     if (!strcmp(name, "krylov_work_bytes")) { g_krylov_work_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "host_chunk_bytes")) { g_host_chunk_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "time_passes")) { g_time_passes = value ? 1 : 0; return TB200_OK; }
