@@ -131,19 +131,23 @@ def c4s():
 
 
 def sweep():
-    """Batched Toeplitz{Float64} matvec across sizes: algorithmic GB/s (read x + write y) at ~512 MiB per operand."""
+    """Batched Toeplitz matvec across sizes: algorithmic GB/s (read x + write y) at ~512 MiB per operand.
+    SWEEP_DTYPE = f64 (default) | f32 | c64 | c128."""
+    name = os.environ.get("SWEEP_DTYPE", "f64")
+    dt = {"f64": torch.float64, "f32": torch.float32, "c64": torch.complex64, "c128": torch.complex128}[name]
+    esz = torch.empty(0, dtype=dt).element_size()
     for ln in range(int(os.environ.get("SWEEP_LO", 8)), int(os.environ.get("SWEEP_HI", 24))):
         n = 1 << ln
-        cols = max(2, min(1 << 20, (512 << 20) // (8 * n)))
+        cols = max(2, min(1 << 20, (512 << 20) // (esz * n)))
         k = np.arange(n, dtype=np.float64)
-        A = tb.Toeplitz(torch.from_numpy(0.9 ** k).cuda(), torch.from_numpy(0.4 ** k).cuda())
+        A = tb.Toeplitz(torch.from_numpy(0.9 ** k).cuda().to(dt), torch.from_numpy(0.4 ** k).cuda().to(dt))
         F = tb.factorize(A)
-        X = tb.colmajor(n, cols); X.copy_(torch.randn(n, cols, dtype=torch.float64, device="cuda"))
-        Y = tb.colmajor(n, cols)
+        X = tb.colmajor(n, cols, dt)
+        X.copy_(torch.randn(n, cols, dtype=dt, device="cuda"))
+        Y = tb.colmajor(n, cols, dt)
         t = timed(lambda: tb.mul_(Y, F, X), 5)
-        info = {}
-        out(config="sweep Toeplitz{Float64} n=2^%d x %d columns" % (ln, cols), matvecs_per_s=cols / t, alg_gbs=2 * 8 * n * cols / t / 1e9,
-            frac_hbm=2 * 8 * n * cols / t / 1e9 / HBM)
+        out(config="sweep Toeplitz{%s} n=2^%d x %d columns" % (name, ln, cols), matvecs_per_s=cols / t,
+            alg_gbs=2 * esz * n * cols / t / 1e9, frac_hbm=2 * esz * n * cols / t / 1e9 / HBM)
         del X, Y, F
 
 

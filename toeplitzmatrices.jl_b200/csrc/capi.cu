@@ -36,7 +36,7 @@ static std::atomic<int> g_overlap_streams{2};   // helper streams for group over
 static std::atomic<int> g_mega{0};               // opt-in persistent single-launch path (measured slower than 3 kernels x 2 streams)
 static std::atomic<int> g_pipe_b{0};             // opt-in cp.async double-buffered persistent pass B (measured slower)
 static std::atomic<int> g_l2max_f64{12}, g_l2max_f32{13}, g_ta_cap{0}, g_force_l1{0};
-static std::atomic<int> g_single_max_f64{13}, g_single_max_f32{13};   // longest embedding done as ONE shared-memory transform (2^k)   // plan tuning knobs
+static std::atomic<int> g_single_max_f64{13}, g_single_max_f32{14};   // longest embedding done as ONE shared-memory transform (2^k)   // plan tuning knobs
 
 // optional per-pass device timing (bench.py's roofline leg): CUDA events recorded on the
 // launching stream around every pass while "time_passes" is on.
