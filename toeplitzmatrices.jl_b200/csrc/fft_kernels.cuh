@@ -73,9 +73,11 @@ struct InView {
 
 template <typename R>
 struct OutView {
-    R* re; R* im; cx<R>* c; int mode; int m_out; int has_beta; R scale; cx<R> alpha, beta;
+    R* re; R* im; cx<R>* c; int mode; int m_out; int has_beta; cx<R> as, beta; bool unit;
     __device__ __forceinline__ OutView(const ConvArgs<R>& p, long long f) {
-        mode = p.y_mode; m_out = (int)p.m_out; has_beta = p.has_beta; scale = p.scale; alpha = p.alpha; beta = p.beta;
+        mode = p.y_mode; m_out = (int)p.m_out; has_beta = p.has_beta; beta = p.beta;
+        as = mk<R>(p.alpha.x * p.scale, p.alpha.y * p.scale);       // alpha/N' folded into one factor
+        unit = !has_beta && as.x == (R)1 && as.y == (R)0;           // pass B of the two-level transform: plain stores
         re = nullptr; im = nullptr; c = nullptr;
         if (mode == IO_CPLX) c = reinterpret_cast<cx<R>*>(p.y) + f * p.ldy;
         else if (mode == IO_REAL) re = reinterpret_cast<R*>(p.y) + f * p.ldy;
@@ -86,17 +88,17 @@ struct OutView {
     }
     __device__ __forceinline__ void store(int idx, cx<R> v) const {
         if (idx >= m_out) return;
-        v.x *= scale; v.y *= scale;
         if (mode == IO_CPLX) {
-            cx<R> o = cmul(alpha, v);
+            if (unit) { c[idx] = v; return; }
+            cx<R> o = cmul(as, v);
             if (has_beta) { const cx<R> b = cmul(beta, c[idx]); o.x += b.x; o.y += b.y; }
             c[idx] = o;
         } else {
-            R o0 = alpha.x * v.x;
+            R o0 = as.x * v.x;
             if (has_beta) o0 = fma(beta.x, re[idx], o0);
             re[idx] = o0;
             if (im) {
-                R o1 = alpha.x * v.y;
+                R o1 = as.x * v.y;
                 if (has_beta) o1 = fma(beta.x, im[idx], o1);
                 im[idx] = o1;
             }
