@@ -495,3 +495,23 @@ def test_levinson_multirhs_shared_recursion(tb, n):
     ref = np.stack([OC.c_levinson_sym(a, Bm[:, j]) for j in range(Bm.shape[1])], axis=1)
     assert rel(X, ref) <= TOL64
     assert rel(X, np.linalg.solve(O.SymmetricToeplitz(a).dense(), Bm)) <= 1e-10
+
+
+@pytest.mark.parametrize("n", [1000, 70000])
+def test_spectrum_transplant_single_gpu(tb, n):
+    """The multi-GPU plumbing on one device: an empty handle that receives another handle's spectrum bytes
+    (what the NCCL broadcast does, sharding.factorize_shared) multiplies exactly like the original."""
+    rng = np.random.default_rng(n)
+    vc, vr = rng.standard_normal(n), rng.standard_normal(n)
+    vr[0] = vc[0]
+    F0 = tb.factorize(tb.Toeplitz(dev(vc), dev(vr)))
+    F1 = tb.factorize_empty_like(0, torch.float64, (n, n))
+    s0, s1 = tb.spectrum_tensor(F0), tb.spectrum_tensor(F1)
+    assert s0.dtype == torch.uint8 and s0.shape == s1.shape and s0.numel() > 0
+    s1.copy_(s0)
+    X = devmat(rng.standard_normal((n, 3)))
+    Y0, Y1 = tb.colmajor(n, 3), tb.colmajor(n, 3)
+    tb.mul_(Y0, F0, X)
+    tb.mul_(Y1, F1, X)
+    assert torch.equal(Y0, Y1)
+    assert rel(host(Y1), O.matvec(O.Toeplitz(vc, vr), host(X))) <= TOL64
