@@ -18,9 +18,15 @@
  *    precision of a handle is that of its matrix (S = promote_type(float(T),
  *    ComplexF32), src/linearalgebra.jl:125): vectors passed to a handle must have the
  *    same precision (real or complex); the host layer casts mixed inputs.
- *  - a handle owns its spectrum, twiddle tables and one workspace: use a handle from
- *    one stream at a time (the reference's factorization has the same restriction
- *    through its shared `tmp`, src/ToeplitzMatrices.jl:97-101).
+ *  - a handle owns its (read-only) spectrum plus one workspace set PER CALLING STREAM: it
+ *    may be used concurrently from several streams / host threads (one stream per thread).
+ *    The reference's factorization cannot -- every product shares its single `tmp` vector
+ *    (src/ToeplitzMatrices.jl:97-101).  A product on a stream other than the one that
+ *    factorized waits for the spectrum by event; no host synchronisation is needed.
+ *  - device memory comes from the stream-ordered pool; tb200_destroy orders the release
+ *    after everything already queued on the streams that used the handle, so destroying
+ *    right after an asynchronous call is safe.  The caller's vectors must outlive the
+ *    work queued on them, as with any asynchronous CUDA call.
  *  - there is NO CPU fallback: unsupported inputs return TB200_UNSUPPORTED.
  */
 #ifndef TOEPLITZ_B200_H
@@ -38,7 +44,8 @@ enum tb200_status {
     TB200_BAD_ARG = 2,        /* -> ArgumentError */
     TB200_UNSUPPORTED = 3,    /* -> ErrorException */
     TB200_CUDA_ERR = 4,
-    TB200_OOM = 5
+    TB200_OOM = 5,
+    TB200_NCCL_ERR = 6
 };
 
 enum tb200_dtype { TB200_F32 = 0, TB200_F64 = 1, TB200_C32 = 2, TB200_C64 = 3 };
@@ -86,8 +93,11 @@ int tb200_info(tb200_handle_t h, int64_t* m, int64_t* n, int64_t* n_embed, int* 
  * (then the real part is taken, src/ToeplitzMatrices.jl:114-115).                      */
 int tb200_mul(tb200_handle_t h, void* y, int64_t ldy, int ydtype, const void* x, int64_t ldx, int xdtype,
               int64_t ncols, const double alpha[2], const double beta[2], void* stream);
-/* same, HOST buffers: column chunks are staged host->device->host through pinned
- * bounce buffers on internal streams, copies overlapped with compute.  Synchronous.  */
+/* same, HOST buffers: column chunks travel host->device->host on three internal streams
+ * (upload / compute / download of consecutive chunks overlap); waits for the handle's
+ * spectrum by event.  Copies are issued straight from / to the caller's memory: pinned
+ * (page-locked) host matrices run at PCIe speed, pageable ones at the driver's staged-copy
+ * speed (both measured in bench.py).  Synchronous.                                     */
 int tb200_mul_host(tb200_handle_t h, void* y_host, int64_t ldy, int ydtype, const void* x_host, int64_t ldx,
                    int xdtype, int64_t ncols, const double alpha[2], const double beta[2]);
 /* N = m+n-1 < 512 direct O(mn) product, no factorization: src/linearalgebra.jl:19-34   */
@@ -167,11 +177,30 @@ int tb200_cg_batched(tb200_handle_t A, tb200_handle_t M, void* X, int64_t ldx, c
                      int* flag, void* stream);
 
 /* ---- multi-GPU plumbing ----------------------------------------------------------------
- * The only exchange on the path is the spectrum, once per factorization: rank 0
- * factorizes, the other ranks create an empty handle of the same shape and the caller
- * broadcasts `bytes` bytes at `ptr` (NCCL over NVLink).             */
+ * Batches shard by columns / systems with no data-path collective; the only
+ * exchange is the spectrum, once per factorization: the root factorizes, the other ranks
+ * create an empty handle of the same shape and the spectrum (`bytes` bytes at `ptr`) is
+ * broadcast over NCCL / NVLink -- by tb200_bcast_spectrum, or by the host's own collective
+ * followed by tb200_spectrum_ready(h, stream_that_wrote_it).                            */
 int tb200_factorize_empty(int kind, int dtype, int64_t m, int64_t n, void* stream, tb200_handle_t* out);
 int tb200_spectrum_buffer(tb200_handle_t h, void** ptr, int64_t* bytes);
+int tb200_spectrum_ready(tb200_handle_t h, void* stream);
+
+/* NCCL communicator (libnccl.so.2 is bound at run time with dlopen; TB200_NCCL_LIB overrides the path).
+ *  tb200_comm_init       one process driving ndev GPUs (devs = NULL: 0..ndev-1), ncclCommInitAll
+ *  tb200_comm_unique_id  128-byte id made on rank 0 and shipped to the other processes by the host
+ *  tb200_comm_init_rank  one process per GPU (the current device), ncclCommInitRank
+ *  tb200_bcast_spectrum  handles[i] lives on local device i of the communicator (nhandles = ndev for
+ *                        tb200_comm_init, 1 for tb200_comm_init_rank); root = rank owning the spectrum;
+ *                        streams[i] (or NULL = default stream) carries the ncclBroadcast and the
+ *                        handle's readiness event.  Asynchronous.                                     */
+typedef struct tb200_comm* tb200_comm_t;
+int tb200_comm_init(int ndev, const int* devs, tb200_comm_t* out);
+int tb200_comm_unique_id(void* id128);
+int tb200_comm_init_rank(int nranks, int rank, const void* id128, tb200_comm_t* out);
+int tb200_comm_size(tb200_comm_t c, int* nranks, int* nlocal);
+int tb200_bcast_spectrum(tb200_comm_t c, tb200_handle_t* handles, int nhandles, int root, void** streams);
+int tb200_comm_destroy(tb200_comm_t c);
 
 /* tuning / introspection: number of kernel launches issued by this library so far      */
 int64_t tb200_launch_count(void);

@@ -12,7 +12,7 @@ from .api import (Toeplitz, SymmetricToeplitz, Circulant, LowerTriangularToeplit
                   Hankel, ToeplitzFactorization, factorize, mul_, mul, ldiv_, ldiv, circ_ldiv_, eigvals, det, inv,
                   pinv, sqrt, circ_mul, adjoint, transpose, strang, chan, durbin, durbin_, levinson, levinson_, trench,
                   cgs, cg, cgs_batched, cg_batched, colmajor, to_colmajor, mul_host_, factorize_host, spectrum_tensor,
-                  factorize_empty_like, launch_count, set_option, pass_times)
+                  factorize_empty_like, spectrum_ready, launch_count, set_option, pass_times)
 from . import containers  # noqa: F401,E402  (also installs + - * == on the matrix types)
 from .containers import (tril, triu, tril_, triu_, reverse, copyto_, fill_, lmul_, rmul_, isdiag, iszero, getindex,  # noqa: F401,E402
                          dense)

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TB200_LIB") or os.path.join(_HERE, "lib", "libtoeplitz_b200.so")   # TB200_LIB: experiment builds
 
-OK, DIM_MISMATCH, BAD_ARG, UNSUPPORTED, CUDA_ERR, OOM = range(6)
+OK, DIM_MISMATCH, BAD_ARG, UNSUPPORTED, CUDA_ERR, OOM, NCCL_ERR = range(7)
 F32, F64, C32, C64 = range(4)
 TOEPLITZ, SYMMETRIC, CIRCULANT, LOWER, UPPER, HANKEL = range(6)
 OP_INV, OP_PINV, OP_SQRT, OP_CONJ, OP_COPY = range(5)
@@ -22,7 +22,9 @@ EXPORTS = [
     "tb200_precond_vector", "tb200_levinson_batched", "tb200_durbin_batched", "tb200_cgs", "tb200_cg",
     "tb200_factorize_empty", "tb200_spectrum_buffer", "tb200_launch_count", "tb200_set_option",
     "tb200_pass_times", "tb200_trench", "tb200_tri_smallinv", "tb200_levinson_multirhs",
-    "tb200_cgs_batched", "tb200_cg_batched",
+    "tb200_cgs_batched", "tb200_cg_batched", "tb200_spectrum_ready",
+    "tb200_comm_init", "tb200_comm_unique_id", "tb200_comm_init_rank", "tb200_comm_size", "tb200_bcast_spectrum",
+    "tb200_comm_destroy",
 ]
 
 
@@ -80,6 +82,13 @@ def lib() -> ctypes.CDLL:
         "tb200_cgs_batched": [vp, vp, vp, i64, vp, i64, ci, i64, i64, ci, dbl, pd, pi, pi, vp],
         "tb200_cg_batched": [vp, vp, vp, i64, vp, i64, ci, i64, i64, ci, dbl, pd, pi, pi, vp],
         "tb200_spectrum_buffer": [vp, pvp, pi64],
+        "tb200_spectrum_ready": [vp, vp],
+        "tb200_comm_init": [ci, pi, pvp],
+        "tb200_comm_unique_id": [vp],
+        "tb200_comm_init_rank": [ci, ci, vp, pvp],
+        "tb200_comm_size": [vp, pi, pi],
+        "tb200_bcast_spectrum": [vp, pvp, ci, ci, pvp],
+        "tb200_comm_destroy": [vp],
         "tb200_set_option": [ctypes.c_char_p, i64],
         "tb200_pass_times": [pd, pi64],
         "tb200_trench": [ci, i64, vp, vp, i64, dbl, vp],

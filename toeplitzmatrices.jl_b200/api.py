@@ -59,7 +59,11 @@ def colmajor(n: int, l: int, dtype=torch.float64, device="cuda") -> torch.Tensor
 
 
 def to_colmajor(X: torch.Tensor) -> torch.Tensor:
-    if X.dim() == 1 or X.stride(0) == 1 and X.stride(1) >= X.shape[0]:
+    """Dense Julia layout: unit stride down a column (any StridedVector / StridedMatrix is accepted by the
+    reference, src/linearalgebra.jl:5,43; the kernels address columns densely, so strided views are packed)."""
+    if X.dim() == 1:
+        return X if (X.stride(0) == 1 or X.shape[0] <= 1) else X.contiguous()
+    if X.stride(0) == 1 and X.stride(1) >= X.shape[0]:
         return X
     out = colmajor(X.shape[0], X.shape[1], X.dtype, X.device)
     out.copy_(X)
@@ -274,6 +278,7 @@ class ToeplitzFactorization:
         self.dtype = dtype          # eltype T of the matrix
         self.shape = shape
         self._keep = keep
+        self.device_index = torch.cuda.current_device() if torch.cuda.is_available() else 0
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -855,6 +860,12 @@ def factorize_empty_like(kind: int, dtype, shape) -> ToeplitzFactorization:
     m, n = shape
     check(L.lib().tb200_factorize_empty(kind, _DT[dtype], m, n, _stream(), ctypes.byref(out)))
     return ToeplitzFactorization(out.value, kind, dtype, (m, n))
+
+
+def spectrum_ready(F: ToeplitzFactorization) -> None:
+    """Tell the handle that its spectrum buffer was (re)written on the current stream (after the host's own
+    collective filled :func:`spectrum_tensor`): products on other streams then wait for it by event."""
+    check(L.lib().tb200_spectrum_ready(F._h, _stream()))
 
 
 def launch_count() -> int:

@@ -15,8 +15,6 @@
 
 #include "capi_internal.h"
 #include "fft_launch.cuh"
-#include "mega_kernel.cuh"
-#include "pipe_kernels.cuh"
 #include "aux_kernels.cuh"
 #include "blas1.cuh"
 #include "krylov_batched.cuh"
@@ -33,8 +31,6 @@ static std::atomic<long long> g_host_chunk_bytes{256ll << 20};
 static std::atomic<long long> g_krylov_work_bytes{16ll << 30};   // work-vector budget of the batched cgs / cg (columns per chunk)
 static std::atomic<int> g_time_passes{0};
 static std::atomic<int> g_overlap_streams{2};   // helper streams for group overlap (0/1 = off)
-static std::atomic<int> g_mega{0};               // opt-in persistent single-launch path (measured slower than 3 kernels x 2 streams)
-static std::atomic<int> g_pipe_b{0};             // opt-in cp.async double-buffered persistent pass B (measured slower)
 static std::atomic<int> g_l2max_f64{12}, g_l2max_f32{13}, g_ta_cap{0}, g_force_l1{0};
 static std::atomic<int> g_single_max_f64{13}, g_single_max_f32{14};   // longest embedding done as ONE shared-memory transform (2^k)   // plan tuning knobs
 
@@ -113,16 +109,46 @@ struct DevBuf {
     cudaStream_t st = nullptr;
     ~DevBuf() { if (p) cudaFreeAsync(p, st); }
 };
-static int dev_alloc(std::shared_ptr<DevBuf>& out, size_t bytes, const char* what) {
+// Ordering rules of the pool (one private allocation stream per device):
+//  * dev_alloc_on(.., s): the block is allocated on the private stream and stream `s` is made to wait for that
+//    allocation (event), so kernels launched on `s` afterwards may use it -- no host synchronisation.
+//  * dev_alloc_sync(..): host-synchronous variant for data that is cached per device and read from ANY stream later
+//    (twiddle tables): the block and its contents are complete when the call returns.
+//  * frees (DevBuf destructor) run on the private stream; before a handle or a workspace is released,
+//    retire_after(s) makes the private stream wait for everything already queued on each stream that used it, so a
+//    block can never be handed out again while a kernel of the old owner is still in flight (tb200_destroy right after
+//    an asynchronous tb200_mul is safe on any stream).
+static int order_stream_after(cudaStream_t waiter, cudaStream_t producer, const char* what) {
+    cudaEvent_t ev = nullptr;
+    TB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), what);
+    cudaError_t e = cudaEventRecord(ev, producer);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(waiter, ev, 0);
+    cudaEventDestroy(ev);                       // released by the runtime once the record has completed
+    return cuda_status(e, what);
+}
+static int retire_after(cudaStream_t user) { return order_stream_after(alloc_stream(), user, "retire ordering"); }
+static int dev_alloc_raw(std::shared_ptr<DevBuf>& out, size_t bytes, const char* what) {
     auto b = std::make_shared<DevBuf>();
     if (bytes == 0) bytes = 16;
     b->st = alloc_stream();
     cudaError_t e = cudaMallocAsync(&b->p, bytes, b->st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(b->st);       // the block is usable from any stream afterwards
     if (e != cudaSuccess) { b->p = nullptr; return cuda_status(e, what); }
     b->bytes = bytes;
     out = b;
     return TB200_OK;
+}
+static int dev_alloc_on(std::shared_ptr<DevBuf>& out, size_t bytes, const char* what, cudaStream_t s) {
+    TB_TRY(dev_alloc_raw(out, bytes, what));
+    return order_stream_after(s, alloc_stream(), what);
+}
+static int dev_alloc_sync(std::shared_ptr<DevBuf>& out, size_t bytes, const char* what) {
+    TB_TRY(dev_alloc_raw(out, bytes, what));
+    return cuda_status(cudaStreamSynchronize(alloc_stream()), what);
+}
+// host -> device upload that is complete (visible to every stream) when the call returns
+static int upload_sync(void* dst, const void* src, size_t bytes, const char* what) {
+    TB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, alloc_stream()), what);
+    return cuda_status(cudaStreamSynchronize(alloc_stream()), what);
 }
 
 static int num_sms() {
@@ -201,8 +227,8 @@ static int stage_twiddles(int log2l, const cx<R>** out) {
                 }
         }
         std::shared_ptr<DevBuf> b;
-        TB_TRY(dev_alloc(b, sizeof(cx<R>) * h.size(), "twiddle table"));
-        TB_CUDA(cudaMemcpy(b->p, h.data(), sizeof(cx<R>) * h.size(), cudaMemcpyHostToDevice), "twiddle upload");
+        TB_TRY(dev_alloc_sync(b, sizeof(cx<R>) * h.size(), "twiddle table"));
+        TB_TRY(upload_sync(b->p, h.data(), sizeof(cx<R>) * h.size(), "twiddle upload"));
         slot = b;
     }
     *out = reinterpret_cast<const cx<R>*>(slot->p);
@@ -216,29 +242,57 @@ using namespace tb;
 // ---------------------------------------------------------------------------------------
 // the handle
 // ---------------------------------------------------------------------------------------
-struct tb200_fact {
-    int kind = 0, dtype = 0, prec = 0, a_real = 0, device = 0;
-    int64_t m = 0, n = 0, Np = 0;
-    int log2np = 0, two_level = 0, log2l1 = 0, log2l2 = 0, ta = 0;
-    int reverse_x = 0;
+// Everything a product needs besides the (read-only) spectrum and twiddle tables, owned PER CALLING STREAM: the
+// two-level workspaces, the helper streams that overlap consecutive column groups, and the Bluestein buffers.  One
+// handle can therefore be used from several streams / host threads at once -- the reference's factorization cannot
+// (its single `tmp` vector is shared by every product, src/ToeplitzMatrices.jl:97-101).
+struct StreamWork {
     static constexpr int MAXS = 4;
-    std::shared_ptr<DevBuf> spec, inv_spec, tw_lo, tw_hi, tw_g, scratch, scratch_extra[MAXS], sched;
-    int tw_hb = 0;
-    bool spec_valid = false;
-    // Bluestein plan (Circulant, n not a power of two): spectrum kept in NATURAL order (n entries)
-    bool bluestein = false;
-    std::shared_ptr<tb200_fact> bs_conv;          // complex symmetric Toeplitz T[d] = exp(+i pi d^2/n)
-    std::shared_ptr<DevBuf> bs_chirp, bs_u, bs_v; // chirp c[j] = exp(-i pi j^2/n); work buffers
-    // two helper streams: consecutive column groups of a two-level product alternate between them so
-    // the tail of one pass overlaps the next group's passes (each stream owns one workspace)
+    std::shared_ptr<DevBuf> scratch, scratch_extra[MAXS], bs_u, bs_v;
     cudaStream_t hs[MAXS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[MAXS] = {nullptr, nullptr, nullptr, nullptr};
-    ~tb200_fact() {
+    ~StreamWork() {
         for (int i = 0; i < MAXS; ++i) {
             if (hs[i]) cudaStreamDestroy(hs[i]);
             if (ev_join[i]) cudaEventDestroy(ev_join[i]);
         }
         if (ev_fork) cudaEventDestroy(ev_fork);
+    }
+};
+
+struct tb200_fact {
+    int kind = 0, dtype = 0, prec = 0, a_real = 0, device = 0;
+    int64_t m = 0, n = 0, Np = 0;
+    int log2np = 0, two_level = 0, log2l1 = 0, log2l2 = 0, ta = 0;
+    int reverse_x = 0;
+    static constexpr int MAXS = StreamWork::MAXS;
+    std::shared_ptr<DevBuf> spec, inv_spec, tw_lo, tw_hi, tw_g;
+    int tw_hb = 0;
+    bool spec_valid = false;
+    // readiness of the spectrum / reciprocal spectrum: recorded on the stream that produced them; a product on any
+    // OTHER stream waits for the event first (tb200_mul_host's internal streams included)
+    cudaEvent_t ev_spec = nullptr, ev_inv = nullptr;
+    cudaStream_t spec_stream = nullptr, inv_stream = nullptr;
+    // Bluestein plan (Circulant, n not a power of two): spectrum kept in NATURAL order (n entries)
+    bool bluestein = false;
+    std::shared_ptr<tb200_fact> bs_conv;          // complex symmetric Toeplitz T[d] = exp(+i pi d^2/n)
+    std::shared_ptr<DevBuf> bs_chirp;             // chirp c[j] = exp(-i pi j^2/n)
+    cudaStream_t host_s[3] = {nullptr, nullptr, nullptr};   // tb200_mul_host: upload / compute / download streams
+    std::mutex mu;                                // guards `works`, inv_spec creation
+    std::vector<std::pair<cudaStream_t, std::unique_ptr<StreamWork>>> works;
+    StreamWork* work_for(cudaStream_t s) {
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto& w : works) if (w.first == s) return w.second.get();
+        works.emplace_back(s, std::unique_ptr<StreamWork>(new StreamWork()));
+        return works.back().second.get();
+    }
+    ~tb200_fact() {
+        // frees are stream-ordered on the pool's private stream: let it wait for everything queued on the streams that
+        // used this handle (helper streams always join their user stream before a call returns)
+        for (auto& w : works) retire_after(w.first);
+        if (ev_spec) { retire_after(spec_stream); cudaEventDestroy(ev_spec); }
+        if (ev_inv) cudaEventDestroy(ev_inv);
+        for (int i = 0; i < 3; ++i) if (host_s[i]) cudaStreamDestroy(host_s[i]);
     }
 };
 
@@ -296,18 +350,18 @@ static int make_plan(tb200_fact* h) {
                 std::vector<cx<double>> lo, hi;
                 fill_twiddles<double>(lo, nlo, 1, 1ll << l);
                 fill_twiddles<double>(hi, nhi, nlo, 1ll << l);
-                TB_TRY(dev_alloc(clo, lo.size() * 16, "level twiddles"));
-                TB_TRY(dev_alloc(chi, hi.size() * 16, "level twiddles"));
-                TB_CUDA(cudaMemcpy(clo->p, lo.data(), lo.size() * 16, cudaMemcpyHostToDevice), "level twiddle upload");
-                TB_CUDA(cudaMemcpy(chi->p, hi.data(), hi.size() * 16, cudaMemcpyHostToDevice), "level twiddle upload");
+                TB_TRY(dev_alloc_sync(clo, lo.size() * 16, "level twiddles"));
+                TB_TRY(dev_alloc_sync(chi, hi.size() * 16, "level twiddles"));
+                TB_TRY(upload_sync(clo->p, lo.data(), lo.size() * 16, "level twiddle upload"));
+                TB_TRY(upload_sync(chi->p, hi.data(), hi.size() * 16, "level twiddle upload"));
             } else {
                 std::vector<cx<float>> lo, hi;
                 fill_twiddles<float>(lo, nlo, 1, 1ll << l);
                 fill_twiddles<float>(hi, nhi, nlo, 1ll << l);
-                TB_TRY(dev_alloc(clo, lo.size() * 8, "level twiddles"));
-                TB_TRY(dev_alloc(chi, hi.size() * 8, "level twiddles"));
-                TB_CUDA(cudaMemcpy(clo->p, lo.data(), lo.size() * 8, cudaMemcpyHostToDevice), "level twiddle upload");
-                TB_CUDA(cudaMemcpy(chi->p, hi.data(), hi.size() * 8, cudaMemcpyHostToDevice), "level twiddle upload");
+                TB_TRY(dev_alloc_sync(clo, lo.size() * 8, "level twiddles"));
+                TB_TRY(dev_alloc_sync(chi, hi.size() * 8, "level twiddles"));
+                TB_TRY(upload_sync(clo->p, lo.data(), lo.size() * 8, "level twiddle upload"));
+                TB_TRY(upload_sync(chi->p, hi.data(), hi.size() * 8, "level twiddle upload"));
             }
         }
         h->tw_lo = clo;
@@ -332,16 +386,16 @@ static int make_plan(tb200_fact* h) {
                     const long double ang = twopi * (long double)nums[e] / (long double)Npl;
                     g[e] = mk<double>((double)cosl(ang), (double)(-sinl(ang)));
                 }
-                TB_TRY(dev_alloc(cg, g.size() * 16, "level twiddle table"));
-                TB_CUDA(cudaMemcpy(cg->p, g.data(), g.size() * 16, cudaMemcpyHostToDevice), "level twiddle upload");
+                TB_TRY(dev_alloc_sync(cg, g.size() * 16, "level twiddle table"));
+                TB_TRY(upload_sync(cg->p, g.data(), g.size() * 16, "level twiddle upload"));
             } else {
                 std::vector<cx<float>> g(nums.size());
                 for (size_t e = 0; e < nums.size(); ++e) {
                     const long double ang = twopi * (long double)nums[e] / (long double)Npl;
                     g[e] = mk<float>((float)cosl(ang), (float)(-sinl(ang)));
                 }
-                TB_TRY(dev_alloc(cg, g.size() * 8, "level twiddle table"));
-                TB_CUDA(cudaMemcpy(cg->p, g.data(), g.size() * 8, cudaMemcpyHostToDevice), "level twiddle upload");
+                TB_TRY(dev_alloc_sync(cg, g.size() * 8, "level twiddle table"));
+                TB_TRY(upload_sync(cg->p, g.data(), g.size() * 8, "level twiddle upload"));
             }
         }
         h->tw_g = cg;
@@ -349,10 +403,24 @@ static int make_plan(tb200_fact* h) {
     return TB200_OK;
 }
 
-static int ensure_scratch(tb200_fact* h, size_t bytes) {
-    if (h->scratch && h->scratch->bytes >= bytes) return TB200_OK;
-    h->scratch.reset();
-    return dev_alloc(h->scratch, bytes, "workspace");
+static int ensure_buf(std::shared_ptr<DevBuf>& b, size_t bytes, const char* what, cudaStream_t s) {
+    if (b && b->bytes >= bytes) return TB200_OK;
+    if (b) { TB_TRY(retire_after(s)); b.reset(); }      // the old block may still be in use by work queued on s
+    return dev_alloc_on(b, bytes, what, s);
+}
+// a product on a stream other than the one that produced the spectrum waits for it
+static int wait_spectrum(tb200_fact* h, const void* spec, cudaStream_t s) {
+    if (h->ev_spec && s != h->spec_stream) TB_CUDA(cudaStreamWaitEvent(s, h->ev_spec, 0), "spectrum ready");
+    if (spec && h->inv_spec && spec == h->inv_spec->p && h->ev_inv && s != h->inv_stream)
+        TB_CUDA(cudaStreamWaitEvent(s, h->ev_inv, 0), "reciprocal spectrum ready");
+    return TB200_OK;
+}
+static int mark_spectrum_ready(tb200_fact* h, cudaStream_t s) {
+    if (!h->ev_spec) TB_CUDA(cudaEventCreateWithFlags(&h->ev_spec, cudaEventDisableTiming), "event");
+    TB_CUDA(cudaEventRecord(h->ev_spec, s), "spectrum ready");
+    h->spec_stream = s;
+    h->spec_valid = true;
+    return TB200_OK;
 }
 
 // One description of "apply a spectrum to columns": covers mul!, ldiv!, factorize's FFT and to_vc.
@@ -382,6 +450,7 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     a.scale = (R)c.scale; a.alpha = mk<R>((R)c.alpha[0], (R)c.alpha[1]); a.beta = mk<R>((R)c.beta[0], (R)c.beta[1]);
     a.has_beta = c.has_beta;
     if (c.nfft <= 0) return TB200_OK;
+    TB_TRY(wait_spectrum(h, c.spec, s));
     if (!h->two_level) {
         count_launch();
         PassTimer pt(3, s);
@@ -389,62 +458,31 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     }
     // ---- two-level: A (strided cols, fwd) -> B (rows: fwd * spec inv) -> C (strided cols, inv)
     const long long Np = h->Np, N1 = 1ll << h->log2l1, N2 = 1ll << h->log2l2;
-    if (g_mega.load() && c.do_fwd && c.do_inv && c.nfft >= 2 && c.spec && c.x_mode != IO_SPEC && c.y_mode != IO_SPEC &&
-        mega_supported<R>(h->log2l1, h->log2l2, h->ta) && c.nfft < (1ll << 20)) {
-        // one persistent cooperative launch for the whole batch (mega_kernel.cuh)
-        const size_t wbytes = (size_t)Np * sizeof(cx<R>);
-        TB_TRY(ensure_scratch(h, wbytes));
-        if (!h->scratch_extra[1] || h->scratch_extra[1]->bytes < wbytes) {
-            h->scratch_extra[1].reset();
-            TB_TRY(dev_alloc(h->scratch_extra[1], wbytes, "second workspace"));
-        }
-        const size_t sbytes = sizeof(unsigned) * (size_t)(4 + 3 * c.nfft);
-        if (!h->sched || h->sched->bytes < sbytes) { h->sched.reset(); TB_TRY(dev_alloc(h->sched, sbytes, "tile scheduler state")); }
-        TB_CUDA(cudaMemsetAsync(h->sched->p, 0, sbytes, s), "scheduler reset");
-        MegaArgs<R> ma;
-        a.log2n2 = h->log2l2;
-        a.tw_lo = reinterpret_cast<const cx<R>*>(h->tw_lo->p);
-        a.tw_hi = reinterpret_cast<const cx<R>*>(h->tw_hi->p);
-        a.tw_hb = h->tw_hb;
-        a.tw_g = reinterpret_cast<const cx<R>*>(h->tw_g->p);
-        ma.c = a;
-        ma.tw_cols = tw_cols; ma.tw_rows = tw_rows;
-        ma.scratch[0] = reinterpret_cast<cx<R>*>(h->scratch->p);
-        ma.scratch[1] = reinterpret_cast<cx<R>*>(h->scratch_extra[1]->p);
-        ma.ticket = reinterpret_cast<unsigned*>(h->sched->p);
-        ma.done = ma.ticket + 4;
-        ma.npairs = c.nfft;
-        count_launch();
-        PassTimer pt(1, s);
-        return cuda_status(launch_mega<R>(h->log2l1, h->log2l2, h->ta, ma, num_sms(), s), "k_mega");
-    }
     long long G = std::max(1ll, g_group_bytes.load() / (long long)(Np * sizeof(cx<R>)));
     G = std::min(G, c.nfft);
-    TB_TRY(ensure_scratch(h, (size_t)G * Np * sizeof(cx<R>)));
+    StreamWork* w = h->work_for(s);
+    TB_TRY(ensure_buf(w->scratch, (size_t)G * Np * sizeof(cx<R>), "workspace", s));
     const int NSTR = g_overlap_streams.load();
     const bool overlap = NSTR >= 2 && c.nfft > G && c.do_fwd && c.do_inv;
     const int nstr = overlap ? NSTR : 1;
     cx<R>* scratch_of[tb200_fact::MAXS];
     cudaStream_t stream_of[tb200_fact::MAXS];
-    for (int i = 0; i < tb200_fact::MAXS; ++i) { scratch_of[i] = reinterpret_cast<cx<R>*>(h->scratch->p); stream_of[i] = s; }
+    for (int i = 0; i < tb200_fact::MAXS; ++i) { scratch_of[i] = reinterpret_cast<cx<R>*>(w->scratch->p); stream_of[i] = s; }
     if (overlap) {
         for (int i = 1; i < nstr; ++i) {
-            if (!h->scratch_extra[i] || h->scratch_extra[i]->bytes < (size_t)G * Np * sizeof(cx<R>)) {
-                h->scratch_extra[i].reset();
-                TB_TRY(dev_alloc(h->scratch_extra[i], (size_t)G * Np * sizeof(cx<R>), "extra workspace"));
-            }
-            scratch_of[i] = reinterpret_cast<cx<R>*>(h->scratch_extra[i]->p);
+            TB_TRY(ensure_buf(w->scratch_extra[i], (size_t)G * Np * sizeof(cx<R>), "extra workspace", s));
+            scratch_of[i] = reinterpret_cast<cx<R>*>(w->scratch_extra[i]->p);
         }
         for (int i = 0; i < nstr; ++i) {
-            if (!h->hs[i]) {
-                TB_CUDA(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking), "helper stream");
-                TB_CUDA(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming), "event");
+            if (!w->hs[i]) {
+                TB_CUDA(cudaStreamCreateWithFlags(&w->hs[i], cudaStreamNonBlocking), "helper stream");
+                TB_CUDA(cudaEventCreateWithFlags(&w->ev_join[i], cudaEventDisableTiming), "event");
             }
-            stream_of[i] = h->hs[i];
+            stream_of[i] = w->hs[i];
         }
-        if (!h->ev_fork) TB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), "event");
-        TB_CUDA(cudaEventRecord(h->ev_fork, s), "fork");
-        for (int i = 0; i < nstr; ++i) TB_CUDA(cudaStreamWaitEvent(h->hs[i], h->ev_fork, 0), "fork");
+        if (!w->ev_fork) TB_CUDA(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming), "event");
+        TB_CUDA(cudaEventRecord(w->ev_fork, s), "fork");
+        for (int i = 0; i < nstr; ++i) TB_CUDA(cudaStreamWaitEvent(w->hs[i], w->ev_fork, 0), "fork");
     }
     cudaStream_t user_stream = s;
     a.log2n2 = h->log2l2;
@@ -492,10 +530,6 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
             }
             count_launch();
             PassTimer pt(1, s);
-            if (g_pipe_b.load() && c.do_fwd && c.do_inv && c.spec && rowsB_pipe_supported<R>(h->log2l2)) {
-                TB_CUDA(launch_rowsB_pipe<R>(h->log2l2, scratch, g * N1, reinterpret_cast<const cx<R>*>(c.spec), (int)N1,
-                                             tw_rows, num_sms(), s), "k_rowsB_pipe");
-            } else
             TB_CUDA(launch_rows<R>(h->log2l2, pb, num_sms(), s), "k_rows (pass B)");
         }
         // pass C
@@ -512,8 +546,8 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     }
     if (overlap) {
         for (int i = 0; i < nstr; ++i) {
-            TB_CUDA(cudaEventRecord(h->ev_join[i], h->hs[i]), "join");
-            TB_CUDA(cudaStreamWaitEvent(user_stream, h->ev_join[i], 0), "join");
+            TB_CUDA(cudaEventRecord(w->ev_join[i], w->hs[i]), "join");
+            TB_CUDA(cudaStreamWaitEvent(user_stream, w->ev_join[i], 0), "join");
         }
     }
     return TB200_OK;
@@ -539,7 +573,7 @@ static int check_factorize_args(int kind, int dtype, int64_t m, int64_t n, const
     return TB200_OK;
 }
 
-static int new_handle(int kind, int dtype, int64_t m, int64_t n, tb200_fact** out) {
+static int new_handle(int kind, int dtype, int64_t m, int64_t n, cudaStream_t s, tb200_fact** out) {
     std::unique_ptr<tb200_fact> h(new tb200_fact());
     h->kind = kind; h->dtype = dtype; h->prec = dt_prec(dtype); h->a_real = !dt_is_cplx(dtype);
     h->m = m; h->n = n;
@@ -549,7 +583,7 @@ static int new_handle(int kind, int dtype, int64_t m, int64_t n, tb200_fact** ou
         if ((n & (n - 1)) != 0 || n < 16) {       // exact n-point DFT semantics through a chirp-z plan
             h->bluestein = true;
             h->reverse_x = 0;
-            TB_TRY(dev_alloc(h->spec, (size_t)n * (h->prec ? 16 : 8), "spectrum"));
+            TB_TRY(dev_alloc_on(h->spec, (size_t)n * (h->prec ? 16 : 8), "spectrum", s));
             *out = h.release();
             return TB200_OK;
         }
@@ -560,7 +594,7 @@ static int new_handle(int kind, int dtype, int64_t m, int64_t n, tb200_fact** ou
     h->log2np = next_log2(h->Np);
     h->reverse_x = (kind == TB200_HANKEL);
     TB_TRY(make_plan(h.get()));
-    TB_TRY(dev_alloc(h->spec, (size_t)h->Np * (h->prec ? 16 : 8), "spectrum"));
+    TB_TRY(dev_alloc_on(h->spec, (size_t)h->Np * (h->prec ? 16 : 8), "spectrum", s));
     *out = h.release();
     return TB200_OK;
 }
@@ -568,8 +602,9 @@ static int new_handle(int kind, int dtype, int64_t m, int64_t n, tb200_fact** ou
 template <typename R>
 static int factorize_t(tb200_fact* h, const void* vc, const void* vr, cudaStream_t s) {
     // K4: embedding into the workspace, then forward FFT into the layout-order spectrum
-    TB_TRY(ensure_scratch(h, (size_t)h->Np * sizeof(cx<R>)));
-    cx<R>* c = reinterpret_cast<cx<R>*>(h->scratch->p);
+    StreamWork* w = h->work_for(s);
+    TB_TRY(ensure_buf(w->scratch, (size_t)h->Np * sizeof(cx<R>), "workspace", s));
+    cx<R>* c = reinterpret_cast<cx<R>*>(w->scratch->p);
     k_embed<R><<<ew_grid(h->Np), 256, 0, s>>>(c, h->Np, h->kind, vc, vr, !h->a_real, h->m, h->n);
     count_launch();
     TB_CUDA(cudaGetLastError(), "k_embed");
@@ -578,8 +613,7 @@ static int factorize_t(tb200_fact* h, const void* vc, const void* vr, cudaStream
     cc.y = h->spec->p; cc.ldy = h->Np; cc.y_mode = IO_SPEC; cc.m_out = h->Np;
     cc.ncols = 1; cc.nfft = 1; cc.do_fwd = 1; cc.do_inv = 0;
     TB_TRY(run_conv_t<R>(h, cc, s));
-    h->spec_valid = true;
-    return TB200_OK;
+    return mark_spectrum_ready(h, s);
 }
 
 static int mode_for(bool cplx) { return cplx ? IO_CPLX : IO_REAL; }
@@ -598,13 +632,13 @@ static int bs_setup_t(tb200_fact* h, cudaStream_t s) {
         c[(size_t)j] = mk<R>((R)cosl(ang), (R)(-sinl(ang)));
         cc[(size_t)j] = mk<R>((R)cosl(ang), (R)sinl(ang));
     }
-    TB_TRY(dev_alloc(h->bs_chirp, sizeof(cx<R>) * (size_t)n, "chirp"));
+    TB_TRY(dev_alloc_on(h->bs_chirp, sizeof(cx<R>) * (size_t)n, "chirp", s));
     TB_CUDA(cudaMemcpyAsync(h->bs_chirp->p, c.data(), sizeof(cx<R>) * (size_t)n, cudaMemcpyHostToDevice, s), "chirp upload");
     std::shared_ptr<DevBuf> tvc;
-    TB_TRY(dev_alloc(tvc, sizeof(cx<R>) * (size_t)n, "chirp filter"));
+    TB_TRY(dev_alloc_on(tvc, sizeof(cx<R>) * (size_t)n, "chirp filter", s));
     TB_CUDA(cudaMemcpyAsync(tvc->p, cc.data(), sizeof(cx<R>) * (size_t)n, cudaMemcpyHostToDevice, s), "chirp filter upload");
     tb200_fact* t = nullptr;
-    TB_TRY(new_handle(TB200_SYMMETRIC, h->prec ? TB200_C64 : TB200_C32, n, n, &t));
+    TB_TRY(new_handle(TB200_SYMMETRIC, h->prec ? TB200_C64 : TB200_C32, n, n, s, &t));
     h->bs_conv.reset(t);
     TB_TRY(factorize_t<R>(t, tvc->p, nullptr, s));
     TB_CUDA(cudaStreamSynchronize(s), "bluestein setup sync");           // host staging vectors go out of scope
@@ -631,9 +665,10 @@ static int bs_run_t(tb200_fact* h, int mode, const void* spec, void* y, int64_t 
     const int64_t n = h->n;
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncols, (64ll << 20) / (int64_t)(n * sizeof(cx<R>))));
     const size_t wbytes = (size_t)chunk * n * sizeof(cx<R>);
-    if (!h->bs_u || h->bs_u->bytes < wbytes) { h->bs_u.reset(); TB_TRY(dev_alloc(h->bs_u, wbytes, "bluestein workspace")); }
-    if (!h->bs_v || h->bs_v->bytes < wbytes) { h->bs_v.reset(); TB_TRY(dev_alloc(h->bs_v, wbytes, "bluestein workspace")); }
-    cx<R>* u = (cx<R>*)h->bs_u->p; cx<R>* v = (cx<R>*)h->bs_v->p;
+    StreamWork* w = h->work_for(s);
+    TB_TRY(ensure_buf(w->bs_u, wbytes, "bluestein workspace", s));
+    TB_TRY(ensure_buf(w->bs_v, wbytes, "bluestein workspace", s));
+    cx<R>* u = (cx<R>*)w->bs_u->p; cx<R>* v = (cx<R>*)w->bs_v->p;
     const cx<R>* chirp = (const cx<R>*)h->bs_chirp->p;
     const cx<R> al = mk<R>((R)(alpha ? alpha[0] : 1.0), (R)(alpha ? alpha[1] : 0.0));
     const cx<R> be = mk<R>((R)(beta ? beta[0] : 0.0), (R)(beta ? beta[1] : 0.0));
@@ -671,8 +706,7 @@ static int bs_run(tb200_fact* h, int mode, const void* spec, void* y, int64_t ld
 static int bs_factorize(tb200_fact* h, const void* vc, cudaStream_t s) {
     TB_TRY(h->prec ? bs_setup_t<double>(h, s) : bs_setup_t<float>(h, s));
     TB_TRY(bs_run(h, 0, nullptr, h->spec->p, h->n, 1, 0, vc, h->n, !h->a_real, 1, nullptr, nullptr, s));
-    h->spec_valid = true;
-    return TB200_OK;
+    return mark_spectrum_ready(h, s);
 }
 
 }  // namespace tb
@@ -699,11 +733,6 @@ int tb200_pass_times(double ms[4], int64_t counts[4]) {
     return TB200_OK;
 }
 
-#ifdef TB_EXP_TRACE
-} namespace tb { cudaError_t debug_set_trace(long long* p); } extern "C" {
-int tb200_debug_set_trace(void* p) { return cuda_status(tb::debug_set_trace((long long*)p), "trace"); }
-#endif
-
 int tb200_set_option(const char* name, int64_t value) {
     if (!name) return set_error(TB200_BAD_ARG, "option name is NULL");
     if (!strcmp(name, "group_bytes")) { g_group_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
@@ -717,8 +746,6 @@ int tb200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "l2max_f32")) { g_l2max_f32 = (int)value; return TB200_OK; }
     if (!strcmp(name, "ta_cap")) { g_ta_cap = (int)value; return TB200_OK; }
     if (!strcmp(name, "force_l1")) { g_force_l1 = (int)value; return TB200_OK; }
-    if (!strcmp(name, "mega")) { g_mega = value ? 1 : 0; return TB200_OK; }
-    if (!strcmp(name, "pipe_b")) { g_pipe_b = value ? 1 : 0; return TB200_OK; }
     return set_error(TB200_BAD_ARG, "unknown option '%s'", name);
 }
 
@@ -727,12 +754,14 @@ int tb200_factorize_empty(int kind, int dtype, int64_t m, int64_t n, void* strea
     if (!out) return set_error(TB200_BAD_ARG, "out is NULL");
     TB_TRY(check_factorize_args(kind, dtype, m, n, nullptr, nullptr, false));
     tb200_fact* h = nullptr;
-    TB_TRY(new_handle(kind, dtype, m, n, &h));
+    TB_TRY(new_handle(kind, dtype, m, n, (cudaStream_t)stream, &h));
     if (h->bluestein) {
         int st = h->prec ? bs_setup_t<double>(h, (cudaStream_t)stream) : bs_setup_t<float>(h, (cudaStream_t)stream);
         if (st != TB200_OK) { delete h; return st; }
     }
-    h->spec_valid = true;          // the caller fills the spectrum buffer (broadcast)
+    // the caller fills the spectrum buffer (tb200_bcast_spectrum, or its own collective followed by
+    // tb200_spectrum_ready on the stream that wrote it)
+    h->spec_valid = true;
     *out = h;
     return TB200_OK;
 }
@@ -742,7 +771,7 @@ int tb200_factorize(int kind, int dtype, int64_t m, int64_t n, const void* vc, c
     if (!out) return set_error(TB200_BAD_ARG, "out is NULL");
     TB_TRY(check_factorize_args(kind, dtype, m, n, vc, vr, true));
     tb200_fact* h = nullptr;
-    TB_TRY(new_handle(kind, dtype, m, n, &h));
+    TB_TRY(new_handle(kind, dtype, m, n, (cudaStream_t)stream, &h));
     int st = h->bluestein ? bs_factorize(h, vc, (cudaStream_t)stream)
            : h->prec ? factorize_t<double>(h, vc, vr, (cudaStream_t)stream) : factorize_t<float>(h, vc, vr, (cudaStream_t)stream);
     if (st != TB200_OK) { delete h; return st; }
@@ -758,10 +787,10 @@ int tb200_factorize_host(int kind, int dtype, int64_t m, int64_t n, const void* 
     const int64_t nvr = (kind == TB200_TOEPLITZ) ? n : 0;
     std::shared_ptr<DevBuf> dvc, dvr;
     cudaStream_t s = (cudaStream_t)stream;
-    TB_TRY(dev_alloc(dvc, (size_t)nvc * esz, "vc staging"));
+    TB_TRY(dev_alloc_on(dvc, (size_t)nvc * esz, "vc staging", s));
     TB_CUDA(cudaMemcpyAsync(dvc->p, vc_host, (size_t)nvc * esz, cudaMemcpyHostToDevice, s), "vc upload");
     if (nvr) {
-        TB_TRY(dev_alloc(dvr, (size_t)nvr * esz, "vr staging"));
+        TB_TRY(dev_alloc_on(dvr, (size_t)nvr * esz, "vr staging", s));
         TB_CUDA(cudaMemcpyAsync(dvr->p, vr_host, (size_t)nvr * esz, cudaMemcpyHostToDevice, s), "vr upload");
     }
     int st = tb200_factorize(kind, dtype, m, n, dvc->p, nvr ? dvr->p : nullptr, stream, out);
@@ -783,6 +812,12 @@ int tb200_info(tb200_handle_t h, int64_t* m, int64_t* n, int64_t* n_embed, int* 
     if (dtype) *dtype = h->dtype;
     if (kind) *kind = h->kind;
     return TB200_OK;
+}
+
+int tb200_spectrum_ready(tb200_handle_t h, void* stream) {
+    DeviceGuard dev_guard(h);
+    if (!h) return set_error(TB200_BAD_ARG, "handle is NULL");
+    return mark_spectrum_ready(h, (cudaStream_t)stream);
 }
 
 int tb200_spectrum_buffer(tb200_handle_t h, void** ptr, int64_t* bytes) {
@@ -870,17 +905,14 @@ int tb200_mul_host(tb200_handle_t h, void* y_host, int64_t ldy, int ydtype, cons
             if (ev_cmp[i]) cudaEventDestroy(ev_cmp[i]);
             if (ev_out[i]) cudaEventDestroy(ev_out[i]);
         }
-        if (s_in) cudaStreamDestroy(s_in);
-        if (s_cmp) cudaStreamDestroy(s_cmp);
-        if (s_out) cudaStreamDestroy(s_out);
     };
 #define TB_HOSTTRY(expr) do { st = (expr); if (st != TB200_OK) { cleanup(); return st; } } while (0)
-    TB_HOSTTRY(cuda_status(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking), "stream"));
-    TB_HOSTTRY(cuda_status(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking), "stream"));
-    TB_HOSTTRY(cuda_status(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking), "stream"));
+    for (int i = 0; i < 3; ++i)
+        if (!h->host_s[i]) TB_HOSTTRY(cuda_status(cudaStreamCreateWithFlags(&h->host_s[i], cudaStreamNonBlocking), "stream"));
+    s_in = h->host_s[0]; s_cmp = h->host_s[1]; s_out = h->host_s[2];
     for (int i = 0; i < NS; ++i) {
-        TB_HOSTTRY(dev_alloc(xd[i], (size_t)cc * h->n * xsz, "host-path x buffer"));
-        TB_HOSTTRY(dev_alloc(yd[i], (size_t)cc * h->m * ysz, "host-path y buffer"));
+        TB_HOSTTRY(dev_alloc_sync(xd[i], (size_t)cc * h->n * xsz, "host-path x buffer"));
+        TB_HOSTTRY(dev_alloc_sync(yd[i], (size_t)cc * h->m * ysz, "host-path y buffer"));
         TB_HOSTTRY(cuda_status(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming), "event"));
         TB_HOSTTRY(cuda_status(cudaEventCreateWithFlags(&ev_cmp[i], cudaEventDisableTiming), "event"));
         TB_HOSTTRY(cuda_status(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming), "event"));
@@ -960,10 +992,15 @@ static int spec_map_launch(tb200_fact* h, void* out, const void* in, int op, dou
 }
 
 static int ensure_inv_spec(tb200_fact* h, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(h->mu);
     if (h->inv_spec) return TB200_OK;
     std::shared_ptr<DevBuf> b;
-    TB_TRY(dev_alloc(b, (size_t)h->Np * (h->prec ? 16 : 8), "reciprocal spectrum"));
+    TB_TRY(dev_alloc_on(b, (size_t)h->Np * (h->prec ? 16 : 8), "reciprocal spectrum", s));
+    TB_TRY(wait_spectrum(h, nullptr, s));
     TB_TRY(spec_map_launch(h, b->p, h->spec->p, OP_INV, 0.0, s));
+    if (!h->ev_inv) TB_CUDA(cudaEventCreateWithFlags(&h->ev_inv, cudaEventDisableTiming), "event");
+    TB_CUDA(cudaEventRecord(h->ev_inv, s), "reciprocal spectrum ready");
+    h->inv_stream = s;
     h->inv_spec = b;
     return TB200_OK;
 }
@@ -983,6 +1020,7 @@ int tb200_circ_spectrum(tb200_handle_t h, void* out, void* stream) {
     TB_TRY(require_circulant(h));
     if (!out) return set_error(TB200_BAD_ARG, "out is NULL");
     cudaStream_t s = (cudaStream_t)stream;
+    TB_TRY(wait_spectrum(h, nullptr, s));
     if (h->bluestein)
         return cuda_status(cudaMemcpyAsync(out, h->spec->p, (size_t)h->n * (h->prec ? 16 : 8), cudaMemcpyDeviceToDevice, s), "spectrum copy");
     const int l1 = h->two_level ? h->log2l1 : 0;
@@ -992,9 +1030,9 @@ int tb200_circ_spectrum(tb200_handle_t h, void* out, void* stream) {
     return cuda_status(cudaGetLastError(), "k_unscramble");
 }
 
-static int clone_plan(tb200_fact* h, tb200_fact** out) {
+static int clone_plan(tb200_fact* h, cudaStream_t s, tb200_fact** out) {
     tb200_fact* g = nullptr;
-    TB_TRY(new_handle(h->kind, h->dtype, h->m, h->n, &g));
+    TB_TRY(new_handle(h->kind, h->dtype, h->m, h->n, s, &g));
     if (h->bluestein) { g->bs_conv = h->bs_conv; g->bs_chirp = h->bs_chirp; }
     *out = g;
     return TB200_OK;
@@ -1006,12 +1044,13 @@ int tb200_circ_map(tb200_handle_t h, int op, double tol, void* stream, tb200_han
     if (!out) return set_error(TB200_BAD_ARG, "out is NULL");
     if (op < 0 || op > 4) return set_error(TB200_BAD_ARG, "unknown spectrum op %d", op);
     tb200_fact* g = nullptr;
-    TB_TRY(clone_plan(h, &g));
-    int st = spec_map_launch(h, g->spec->p, h->spec->p, op, tol, (cudaStream_t)stream);
+    TB_TRY(clone_plan(h, (cudaStream_t)stream, &g));
+    int st = wait_spectrum(h, nullptr, (cudaStream_t)stream);
+    if (st == TB200_OK) st = spec_map_launch(h, g->spec->p, h->spec->p, op, tol, (cudaStream_t)stream);
+    if (st == TB200_OK) st = mark_spectrum_ready(g, (cudaStream_t)stream);
     if (st != TB200_OK) { delete g; return st; }
     // sqrt/inv/pinv/conj of a real circulant's spectrum stay Hermitian only for inv/pinv/conj; sqrt of a
     // spectrum with negative real eigenvalues does not, but the reference takes maybereal anyway (:314).
-    g->spec_valid = true;
     *out = g;
     return TB200_OK;
 }
@@ -1027,15 +1066,17 @@ int tb200_circ_mul(tb200_handle_t a, tb200_handle_t b, void* stream, tb200_handl
     if (a->prec != b->prec) return set_error(TB200_BAD_ARG, "precision mismatch between the two factorizations");
     tb200_fact* g = nullptr;
     const int dt = (dt_is_cplx(a->dtype) || dt_is_cplx(b->dtype)) ? (a->prec ? TB200_C64 : TB200_C32) : a->dtype;
-    TB_TRY(new_handle(TB200_CIRCULANT, dt, a->n, a->n, &g));
-    if (a->bluestein) { g->bs_conv = a->bs_conv; g->bs_chirp = a->bs_chirp; }
     cudaStream_t s = (cudaStream_t)stream;
+    TB_TRY(new_handle(TB200_CIRCULANT, dt, a->n, a->n, s, &g));
+    if (a->bluestein) { g->bs_conv = a->bs_conv; g->bs_chirp = a->bs_chirp; }
+    TB_TRY(wait_spectrum(a, nullptr, s));
+    TB_TRY(wait_spectrum(b, nullptr, s));
     if (a->prec) k_spec_mul<double><<<ew_grid(a->Np), 256, 0, s>>>((cx<double>*)g->spec->p, (const cx<double>*)a->spec->p, (const cx<double>*)b->spec->p, a->Np);
     else k_spec_mul<float><<<ew_grid(a->Np), 256, 0, s>>>((cx<float>*)g->spec->p, (const cx<float>*)a->spec->p, (const cx<float>*)b->spec->p, a->Np);
     count_launch();
     int st = cuda_status(cudaGetLastError(), "k_spec_mul");
+    if (st == TB200_OK) st = mark_spectrum_ready(g, s);
     if (st != TB200_OK) { delete g; return st; }
-    g->spec_valid = true;
     *out = g;
     return TB200_OK;
 }
@@ -1097,7 +1138,7 @@ int tb200_levinson_multirhs(int dtype, int64_t n, int64_t nrhs, const void* vc, 
     cudaStream_t s = (cudaStream_t)stream;
     const size_t esz = dt_prec(dtype) ? 8 : 4;
     std::shared_ptr<DevBuf> work;
-    TB_TRY(dev_alloc(work, esz * (size_t)(n * ((n + 127) / 128 * 128) + 2 * n + 8), "levinson y-table"));
+    TB_TRY(dev_alloc_on(work, esz * (size_t)(n * ((n + 127) / 128 * 128) + 2 * n + 8), "levinson y-table", s));
     TB_TRY(levinson_multirhs_dispatch(dtype, n, nrhs, vc, B, ldb, X, ldx, work->p, s));
     TB_CUDA(cudaStreamSynchronize(s), "levinson multi-RHS sync");     // the table is released on return
     return TB200_OK;
@@ -1122,8 +1163,8 @@ int tb200_trench(int dtype, int64_t n, const void* r, void* B, int64_t ldb, doub
     cudaStream_t s = (cudaStream_t)stream;
     const size_t esz = dt_prec(dtype) ? 8 : 4;
     std::shared_ptr<DevBuf> ybuf, scal;
-    TB_TRY(dev_alloc(ybuf, esz * (size_t)std::max<int64_t>(n - 1, 1), "trench durbin vector"));
-    TB_TRY(dev_alloc(scal, sizeof(double) * 4 * 64 + 64, "trench scalars"));
+    TB_TRY(dev_alloc_on(ybuf, esz * (size_t)std::max<int64_t>(n - 1, 1), "trench durbin vector", s));
+    TB_TRY(dev_alloc_on(scal, sizeof(double) * 4 * 64 + 64, "trench scalars", s));
     double* dots = (double*)scal->p;
     double* partials = dots + 4;
     unsigned* counter = (unsigned*)(partials + 4 * 60);
@@ -1160,9 +1201,9 @@ struct KrylovCtx {
     double host_out[4];
 
     int init() {
-        TB_TRY(dev_alloc(partials, sizeof(double) * 4 * 4096, "dot partials"));
-        TB_TRY(dev_alloc(counter, 16, "dot counter"));
-        TB_TRY(dev_alloc(out, sizeof(double) * 4, "dot result"));
+        TB_TRY(dev_alloc_on(partials, sizeof(double) * 4 * 4096, "dot partials", s));
+        TB_TRY(dev_alloc_on(counter, 16, "dot counter", s));
+        TB_TRY(dev_alloc_on(out, sizeof(double) * 4, "dot result", s));
         TB_CUDA(cudaMemsetAsync(counter->p, 0, 16, s), "memset");
         return TB200_OK;
     }
@@ -1223,7 +1264,7 @@ static int cgs_t(tb200_fact* A, tb200_fact* M, T* x, const T* b, int dtype, int6
     KrylovCtx<T> k{A, M, dtype, n, s};
     TB_TRY(k.init());
     std::shared_ptr<DevBuf> buf;
-    TB_TRY(dev_alloc(buf, sizeof(T) * (size_t)n * 8, "cgs work vectors"));
+    TB_TRY(dev_alloc_on(buf, sizeof(T) * (size_t)n * 8, "cgs work vectors", s));
     T* u = (T*)buf->p; T* p = u + n; T* ph = p + n; T* q = ph + n; T* uh = q + n; T* vh = uh + n; T* r = vh + n; T* rt = r + n;
     TB_CUDA(cudaMemsetAsync(buf->p, 0, sizeof(T) * (size_t)n * 6, s), "memset");       // u,p,ph,q,uh,vh = zeros (:141-146)
     const unsigned grid = ew_grid(n);
@@ -1280,7 +1321,7 @@ static int cg_t(tb200_fact* A, tb200_fact* M, T* x, const T* b, int dtype, int64
     KrylovCtx<T> k{A, M, dtype, n, s};
     TB_TRY(k.init());
     std::shared_ptr<DevBuf> buf;
-    TB_TRY(dev_alloc(buf, sizeof(T) * (size_t)n * 4, "cg work vectors"));
+    TB_TRY(dev_alloc_on(buf, sizeof(T) * (size_t)n * 4, "cg work vectors", s));
     T* z = (T*)buf->p; T* q = z + n; T* p = q + n; T* r = p + n;
     TB_CUDA(cudaMemsetAsync(buf->p, 0, sizeof(T) * (size_t)n * 3, s), "memset");
     const unsigned grid = ew_grid(n);
@@ -1329,12 +1370,12 @@ static int krylov_batched_t(bool is_cg, tb200_fact* A, tb200_fact* M, T* X, int6
     chunk = std::min<int64_t>(std::min<int64_t>(chunk, nrhs), 65535);
     if (chunk > 1 && (chunk & 1)) --chunk;                       // keep real columns paired in the transforms
     std::shared_ptr<DevBuf> work, stbuf, partials, counters, nact;
-    TB_TRY(dev_alloc(work, sizeof(T) * (size_t)n * (size_t)chunk * nvec, "batched Krylov work vectors"));
+    TB_TRY(dev_alloc_on(work, sizeof(T) * (size_t)n * (size_t)chunk * nvec, "batched Krylov work vectors", s));
     const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>(128, (n + 2047) / 2048));
-    TB_TRY(dev_alloc(stbuf, sizeof(KState) * (size_t)chunk, "Krylov state"));
-    TB_TRY(dev_alloc(partials, sizeof(double) * 4 * gx * (size_t)chunk, "dot partials"));
-    TB_TRY(dev_alloc(counters, sizeof(unsigned) * (size_t)chunk, "dot counters"));
-    TB_TRY(dev_alloc(nact, sizeof(int), "active counter"));
+    TB_TRY(dev_alloc_on(stbuf, sizeof(KState) * (size_t)chunk, "Krylov state", s));
+    TB_TRY(dev_alloc_on(partials, sizeof(double) * 4 * gx * (size_t)chunk, "dot partials", s));
+    TB_TRY(dev_alloc_on(counters, sizeof(unsigned) * (size_t)chunk, "dot counters", s));
+    TB_TRY(dev_alloc_on(nact, sizeof(int), "active counter", s));
     KState* st = (KState*)stbuf->p;
     std::vector<KState> host_st((size_t)chunk);
     const double one[2] = {1, 0}, zero[2] = {0, 0}, minus[2] = {-1, 0};

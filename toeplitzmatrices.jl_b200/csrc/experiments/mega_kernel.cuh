@@ -11,7 +11,7 @@
 // Deadlock freedom: tickets are claimed in order, a tile waits only on tiles with smaller tickets,
 // and every claimed tile is held by a resident CTA (cooperative launch guarantees co-residency).
 #pragma once
-#include "fft_kernels.cuh"
+#include "../fft_kernels.cuh"
 
 namespace tb {
 

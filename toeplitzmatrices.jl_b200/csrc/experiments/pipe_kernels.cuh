@@ -3,7 +3,7 @@
 // spectrum row into S, so no warp ever waits on global-memory latency (the three-kernel path spends
 // ~45 % of pass B in exactly that wait, profiles/experiments_r01.md).  192 KiB shared memory per CTA.
 #pragma once
-#include "fft_kernels.cuh"
+#include "../fft_kernels.cuh"
 
 namespace tb {
 

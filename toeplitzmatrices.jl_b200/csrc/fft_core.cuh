@@ -98,9 +98,6 @@ __device__ __forceinline__ cx<R> mul_w16(cx<R> d, int k) {
 // In-register radix-RAD DIF butterfly: natural in -> a[brev(c)] = X[c].
 template <typename R, int RAD>
 __device__ __forceinline__ void dif_regs(cx<R>* a) {
-#ifdef TB_EXP_NO_BFLY
-    return;
-#endif
 #pragma unroll
     for (int h = RAD / 2; h >= 1; h >>= 1) {
 #pragma unroll
@@ -117,9 +114,6 @@ __device__ __forceinline__ void dif_regs(cx<R>* a) {
 // Mirror: a[brev(c)] = X[c] in -> natural out, conjugate twiddles (unnormalised inverse).
 template <typename R, int RAD>
 __device__ __forceinline__ void dit_regs(cx<R>* a) {
-#ifdef TB_EXP_NO_BFLY
-    return;
-#endif
 #pragma unroll
     for (int h = 1; h <= RAD / 2; h <<= 1) {
 #pragma unroll
@@ -203,13 +197,8 @@ __device__ __forceinline__ float ld_stream(const float* p) {
     return r;
 }
 
-#ifdef TB_EXP_NO_SMEM      // timing experiment only: drop the shared-memory traffic (wrong results)
-#define TB_SM_LOAD(dst, src) (void)0
-#define TB_SM_STORE(dst, src) (void)0
-#else
 #define TB_SM_LOAD(dst, src) dst = src
 #define TB_SM_STORE(dst, src) dst = src
-#endif
 
 // One L-point FFT held by NT threads (t = 0..NT-1), E = 2^LE complex registers each.
 template <typename R, int LOG2L, int LE = le_of<R>()>

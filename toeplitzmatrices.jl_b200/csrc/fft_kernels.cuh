@@ -115,21 +115,6 @@ constexpr int min_ctas(int threads, int smem_bytes) {
     return m < 1 ? 1 : m;
 }
 
-#ifdef TB_EXP_TRACE          // experiment: per-warp phase timestamps of k_rows (profiles/tools/trace_rows.py)
-__device__ long long* g_trace_buf = nullptr;
-__device__ __forceinline__ void trace_mark(int slot) {
-    if (g_trace_buf && (threadIdx.x & 31) == 0) {
-        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        long long* rec = g_trace_buf + ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8;
-        rec[slot] = clock64();
-        if (slot == 0) rec[7] = smid;
-    }
-}
-#define TB_TRACE(slot) trace_mark(slot)
-#else
-#define TB_TRACE(slot) (void)0
-#endif
-
 // ---- contiguous transforms -------------------------------------------------------------
 template <typename R, int LOG2L, int TS>
 __global__ void __launch_bounds__((1 << (LOG2L - le_of<R>())) * TS, min_ctas<R>((1 << (LOG2L - le_of<R>())) * TS, (int)sizeof(cx<R>) * (1 << LOG2L) * TS))
@@ -146,7 +131,6 @@ k_rows(const ConvArgs<R> p) {
         const bool live = f < p.nfft;
         const long long fc = live ? f : 0;          // dead slots run on slot 0's data, never store
         cx<R> a[E];
-        TB_TRACE(0);
         const cx<R>* srow = p.spec ? p.spec + (fc % p.spec_rows) * (long long)L + t : nullptr;
         if (p.x_mode == IO_SPEC) {
             const cx<R>* xin = reinterpret_cast<const cx<R>*>(p.x) + fc * (long long)L + t;
@@ -157,26 +141,12 @@ k_rows(const ConvArgs<R> p) {
 #pragma unroll
             for (int c = 0; c < E; ++c) a[c] = in.load(t + c * NT);
         }
-#ifdef TB_EXP_TRACE
-        if (a[0].x == 123.456 && a[E - 1].y == 654.321) a[1].x += 1;   // force the loads to land before the mark
-#endif
-        TB_TRACE(1);
         if (p.do_fwd) F::forward(a, t, sm, map, p.tw);
-        TB_TRACE(2);
         if (srow) {
 #pragma unroll
-#ifdef TB_EXP_NO_SPEC
-            for (int i = 0; i < E; ++i) a[i] = cmul(a[i], ld_stream(srow + (i & 1)));
-#else
             for (int i = 0; i < E; ++i) a[i] = cmul(a[i], ld_stream(srow + i * NT));
-#endif
         }
-#ifdef TB_EXP_TRACE
-        if (a[0].x == 123.456 && a[E - 1].y == 654.321) a[1].x += 1;
-#endif
-        TB_TRACE(3);
         if (p.do_inv) F::inverse(a, t, sm, map, p.tw);
-        TB_TRACE(4);
         if (live) {
             if (p.y_mode == IO_SPEC) {
                 cx<R>* o = reinterpret_cast<cx<R>*>(p.y) + f * (long long)L + t;
@@ -188,7 +158,6 @@ k_rows(const ConvArgs<R> p) {
                 for (int j = 0; j < E; ++j) out.store(t + j * NT, a[j]);
             }
         }
-        TB_TRACE(5);
         __syncthreads();
     }
 }
@@ -196,13 +165,9 @@ k_rows(const ConvArgs<R> p) {
 // ---- two-level, strided passes -----------------------------------------------------------
 template <typename R>
 __device__ __forceinline__ cx<R> level_twiddle(const ConvArgs<R>& p, unsigned m) {
-#ifdef TB_EXP_NO_LEVEL_TW
-    return __ldg(p.tw_lo + (m & 1u));
-#else
     const cx<R> lo = __ldg(p.tw_lo + (m & ((1u << p.tw_hb) - 1u)));
     const cx<R> hi = __ldg(p.tw_hi + (m >> p.tw_hb));
     return cmul(lo, hi);
-#endif
 }
 
 template <typename R, class F>

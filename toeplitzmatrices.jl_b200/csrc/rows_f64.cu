@@ -15,7 +15,4 @@ template <> cudaError_t launch_rows<double>(int log2l, const ConvArgs<double>& a
     default: return cudaErrorInvalidValue;
     }
 }
-#ifdef TB_EXP_TRACE
-cudaError_t debug_set_trace(long long* p) { return cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)); }
-#endif
 }  // namespace tb

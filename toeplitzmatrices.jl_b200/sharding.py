@@ -59,7 +59,76 @@ def factorize_shared(make_matrix, kind: int, dtype, shape, src: int = 0, group=N
     torch.cuda.synchronize()
     broadcast_bytes(api.spectrum_tensor(F), src, group)
     torch.cuda.synchronize()
+    api.spectrum_ready(F)
     return F
+
+
+class Communicator:
+    """The C ABI's own NCCL communicator (``tb200_comm_*``): what a non-torch host (the Julia extension) uses to
+    broadcast the spectrum.  ``Communicator.all_local(ndev)`` = one process driving ``ndev`` GPUs;
+    ``Communicator.from_torch_group()`` = one process per GPU, the 128-byte NCCL id shipped through the existing
+    ``torch.distributed`` group (any host-side transport does)."""
+
+    def __init__(self, handle):
+        self._c = handle
+
+    @classmethod
+    def all_local(cls, ndev: int, devices=None):
+        import ctypes
+        from . import _lib as L
+        out = ctypes.c_void_p()
+        devs = (ctypes.c_int * ndev)(*(devices if devices is not None else range(ndev)))
+        L.check(L.lib().tb200_comm_init(ndev, devs, ctypes.byref(out)))
+        return cls(out.value)
+
+    @classmethod
+    def from_torch_group(cls, group=None):
+        import ctypes
+        from . import _lib as L
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        ident = ctypes.create_string_buffer(128)
+        if rank == 0:
+            L.check(L.lib().tb200_comm_unique_id(ident))
+        box = [bytes(ident.raw)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        out = ctypes.c_void_p()
+        L.check(L.lib().tb200_comm_init_rank(world, rank, box[0], ctypes.byref(out)))
+        return cls(out.value)
+
+    def size(self):
+        import ctypes
+        from . import _lib as L
+        a, b = ctypes.c_int(), ctypes.c_int()
+        L.check(L.lib().tb200_comm_size(self._c, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def bcast_spectrum(self, factorizations, root: int = 0, streams=None) -> None:
+        """``factorizations[i]`` lives on local device i of the communicator (a single factorization in the
+        one-process-per-GPU mode)."""
+        import ctypes
+        from . import _lib as L
+        fs = list(factorizations) if isinstance(factorizations, (list, tuple)) else [factorizations]
+        hs = (ctypes.c_void_p * len(fs))(*[f._h for f in fs])
+        if streams is None:
+            streams = []
+            for f in fs:
+                with torch.cuda.device(f.device_index):
+                    streams.append(torch.cuda.current_stream().cuda_stream)
+        st = (ctypes.c_void_p * len(fs))(*streams)
+        L.check(L.lib().tb200_bcast_spectrum(self._c, hs, len(fs), root, st))
+
+    def destroy(self) -> None:
+        from . import _lib as L
+        if self._c:
+            L.lib().tb200_comm_destroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
 
 
 def sharded_mul_(Y_local: torch.Tensor, F, X_local: torch.Tensor, alpha=True, beta=False) -> torch.Tensor:
