@@ -142,3 +142,34 @@ def test_batched_chunking_and_errors(tb):
     assert set(f0) == {fo} == {-1} and set(i0) == {ito} == {0} and abs(e0[0] - eo) <= 1e-12
     _, _, i0, f0 = tb.cg_batched(Ad, X0, _devmat(B), Md, 0, tol)
     assert set(f0) == {1} and set(i0) == {0}
+
+
+@pytest.mark.parametrize("n,l", [(6000, 7), (40000, 5)])
+def test_batched_two_level_transforms_with_stragglers(tb, n, l):
+    """Embeddings beyond one shared-memory transform (two-level path, several column groups per product): the column
+    selection and the per-column alpha of the fused residual update must address the same user columns in every group."""
+    rng = np.random.default_rng(25)
+    vc, vr = _p(0.9, n, np.float64), _p(0.4, n, np.float64)
+    Ao, Ad = O.Toeplitz(vc, vr), tb.Toeplitz(_dev(vc), _dev(vr))
+    B = rng.standard_normal((n, l))
+    B[:, 1] = 0
+    B[:, 3] = Ao.dense()[:, 0] if n <= 8000 else O.matvec(Ao, np.eye(1, n, 0).ravel())
+    tol = 100 * np.finfo(np.float64).eps
+    Mo, Md = O.factorize(O.strang(Ao)), tb.factorize(tb.strang(Ad))
+    tb.set_option("group_bytes", 1 << 20)                     # one pair per group -> several groups per product
+    try:
+        X = tb.colmajor(n, l)
+        X.zero_()
+        X, errs, its, flags = tb.cgs_batched(Ad, X, _devmat(B), Md, 12, tol)
+    finally:
+        tb.set_option("group_bytes", 48 << 20)
+    Xh = X.cpu().numpy()
+    for j in range(l):
+        xo, eo, ito, fo = O.cgs(Ao, np.zeros(n), B[:, j].copy(), Mo, 12, tol)
+        assert abs(its[j] - ito) <= 1, (j, its[j], ito)
+        if flags[j] == fo == 0:
+            assert _rel(Xh[:, j], xo) <= 1e-10, j
+        assert np.isfinite(errs[j]) and errs[j] <= max(1e3 * eo, 1e-9), (j, errs[j], eo)
+    # single-vector solver == one-column batched solver
+    x1, e1, i1, f1 = tb.cgs(Ad, torch.zeros(n, dtype=torch.float64, device="cuda"), _dev(B[:, 0].copy()), Md, 12, tol)
+    assert i1 == its[0] and f1 == flags[0] and _rel(x1.cpu().numpy(), Xh[:, 0]) <= 1e-12

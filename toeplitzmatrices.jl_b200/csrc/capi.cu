@@ -13,6 +13,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda.h>
+
 #include "capi_internal.h"
 #include "fft_launch.cuh"
 #include "aux_kernels.cuh"
@@ -30,6 +32,9 @@ static std::atomic<long long> g_group_bytes{48ll << 20};   // two-level scratch 
 static std::atomic<long long> g_host_chunk_bytes{256ll << 20};
 static std::atomic<long long> g_krylov_work_bytes{16ll << 30};   // work-vector budget of the batched cgs / cg (columns per chunk)
 static std::atomic<int> g_time_passes{0};
+static std::atomic<int> g_l2_persist_mb{0};      // persisting-L2 carve-out for the two-level workspaces (0 = off)
+static std::atomic<int> g_tma{0};                // TMA-staged strided passes (tma_cols.cuh) where eligible; measured, see DESIGN.md
+int g_prune_half = 1;                            // pruned pass A / pass C when half of the embedding is padding
 static std::atomic<int> g_overlap_streams{2};   // helper streams for group overlap (0/1 = off)
 static std::atomic<int> g_l2max_f64{12}, g_l2max_f32{13}, g_ta_cap{0}, g_force_l1{0};
 static std::atomic<int> g_single_max_f64{13}, g_single_max_f32{14};   // longest embedding done as ONE shared-memory transform (2^k)   // plan tuning knobs
@@ -403,6 +408,37 @@ static int make_plan(tb200_fact* h) {
     return TB200_OK;
 }
 
+// Persisting-L2 access window on a stream's workspace: its lines are kept (hitProp persisting) while the streamed
+// x / y columns of the same kernels pass through the rest of the cache -- the workspace is written by pass A,
+// rewritten by pass B and read by pass C, and must not be evicted in between by 16 MiB of x and y per column pair.
+static void apply_l2_window(cudaStream_t st, void* base, size_t bytes, int nwindows) {
+    const int mb = g_l2_persist_mb.load();
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    if (mb > 0 && base) {
+        int dev = 0, max_persist = 0, max_window = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        size_t want = std::min<size_t>((size_t)mb << 20, (size_t)std::max(max_persist, 0));
+        static std::atomic<long long> applied[64];
+        if (applied[dev & 63].exchange((long long)want) != (long long)want) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        const size_t wbytes = std::min<size_t>(bytes, (size_t)std::max(max_window, 0));
+        const double share = (double)want / (double)std::max<size_t>(wbytes * (size_t)std::max(nwindows, 1), 1);
+        v.accessPolicyWindow.base_ptr = base;
+        v.accessPolicyWindow.num_bytes = wbytes;
+        v.accessPolicyWindow.hitRatio = (float)std::min(1.0, share);
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } else {
+        v.accessPolicyWindow.num_bytes = 0;
+        v.accessPolicyWindow.hitRatio = 0.f;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+}
+
 static int ensure_buf(std::shared_ptr<DevBuf>& b, size_t bytes, const char* what, cudaStream_t s) {
     if (b && b->bytes >= bytes) return TB200_OK;
     if (b) { TB_TRY(retire_after(s)); b.reset(); }      // the old block may still be in use by work queued on s
@@ -431,7 +467,33 @@ struct ConvCall {
     const void* spec = nullptr;      // layout-order spectrum or null
     int do_fwd = 1, do_inv = 1;
     double scale = 1.0; double alpha[2] = {1, 0}, beta[2] = {0, 0}; int has_beta = 0;
+    const int* colmap = nullptr;                    // device: user column of logical column j (NULL = identity)
+    const double* col_alpha = nullptr; int col_alpha_stride = 0;   // device: per-user-column factor on alpha
 };
+
+// 3-D tensor map over a column-major matrix seen as [column][row of N2 elements][N2 elements], in 8-byte units
+// (tma_cols.cuh).  Returns false when the driver entry point is missing or the layout is not expressible.
+static bool make_cols_tensor_map(CUtensorMap* map, const void* base, int units_per_elem, long long N2, long long rows,
+                                 long long ncols, long long ld_elems, int ta, int box_rows, int box_cols) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeFn>(p);
+    }();
+    if (!fn || rows <= 0 || ncols <= 0) return false;
+    const size_t col_stride = (size_t)ld_elems * (size_t)units_per_elem * 8;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (col_stride & 15)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)(N2 * units_per_elem), (cuuint64_t)rows, (cuuint64_t)ncols};
+    const cuuint64_t strides[2] = {(cuuint64_t)(N2 * units_per_elem * 8), (cuuint64_t)col_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)(ta * units_per_elem), (cuuint32_t)box_rows, (cuuint32_t)box_cols};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 template <typename R>
 static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
@@ -449,6 +511,7 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     a.do_fwd = c.do_fwd; a.do_inv = c.do_inv;
     a.scale = (R)c.scale; a.alpha = mk<R>((R)c.alpha[0], (R)c.alpha[1]); a.beta = mk<R>((R)c.beta[0], (R)c.beta[1]);
     a.has_beta = c.has_beta;
+    a.colmap = c.colmap; a.col_alpha = c.col_alpha; a.col_alpha_stride = c.col_alpha_stride;
     if (c.nfft <= 0) return TB200_OK;
     TB_TRY(wait_spectrum(h, c.spec, s));
     if (!h->two_level) {
@@ -485,6 +548,8 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
         for (int i = 0; i < nstr; ++i) TB_CUDA(cudaStreamWaitEvent(w->hs[i], w->ev_fork, 0), "fork");
     }
     cudaStream_t user_stream = s;
+    const bool l2win = g_l2_persist_mb.load() > 0;
+    if (l2win) for (int i = 0; i < nstr; ++i) apply_l2_window(stream_of[i], scratch_of[i], (size_t)G * Np * sizeof(cx<R>), nstr);
     a.log2n2 = h->log2l2;
     a.tw_lo = reinterpret_cast<const cx<R>*>(h->tw_lo->p);
     a.tw_hi = reinterpret_cast<const cx<R>*>(h->tw_hi->p);
@@ -493,6 +558,34 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     const size_t in_esz = (c.x_mode == IO_REAL || c.x_mode == IO_PAIR) ? sizeof(R) : sizeof(cx<R>);
     const size_t out_esz = (c.y_mode == IO_REAL || c.y_mode == IO_PAIR) ? sizeof(R) : sizeof(cx<R>);
     const long long cols_per_fft = (c.x_mode == IO_PAIR || c.y_mode == IO_PAIR) ? 2 : 1;
+    // ---- optional TMA staging of the strided tiles (tma_cols.cuh) ----
+    alignas(64) CUtensorMap xmap, ymap;
+    bool tmaA = false, tmaC = false;
+    TmaLaunch tlA{0, 0, false, false}, tlC{0, 0, false, false};
+    if (g_tma.load() && !c.colmap && !c.col_alpha && sizeof(R) * 2 >= 8) {
+        const long long halfN = Np / 2;
+        auto tile_rows = [&](bool half) { return (int)std::min<long long>(half ? N1 / 2 : N1, 256); };
+        if ((g_tma.load() & 1) && c.do_fwd && (c.x_mode == IO_CPLX || (c.x_mode == IO_PAIR && sizeof(R) == 8)) && c.n_in % N2 == 0) {
+            const bool pair = c.x_mode == IO_PAIR;
+            const bool half = g_prune_half && c.n_in <= halfN && h->log2l1 >= 4;
+            if (cols_tma_supported<R>(h->log2l1, h->ta, pair) && (!c.reverse_x || c.n_in / N2 <= (half ? N1 / 2 : N1)) &&
+                make_cols_tensor_map(&xmap, c.x, pair ? 1 : (int)(sizeof(cx<R>) / 8), N2, c.n_in / N2, c.ncols, c.ldx, h->ta,
+                                     tile_rows(half), pair ? 2 : 1)) {
+                tmaA = true;
+                tlA = TmaLaunch{(int)(c.n_in / N2), 0, half, pair};
+            }
+        }
+        if ((g_tma.load() & 2) && c.do_inv && !c.has_beta && (c.y_mode == IO_CPLX || (c.y_mode == IO_PAIR && sizeof(R) == 8)) && c.m_out % N2 == 0) {
+            const bool pair = c.y_mode == IO_PAIR;
+            const bool half = g_prune_half && c.m_out <= halfN && h->log2l1 >= 4;
+            if (cols_tma_supported<R>(h->log2l1, h->ta, pair) &&
+                make_cols_tensor_map(&ymap, c.y, pair ? 1 : (int)(sizeof(cx<R>) / 8), N2, c.m_out / N2, c.ncols, c.ldy, h->ta,
+                                     tile_rows(half), pair ? 2 : 1)) {
+                tmaC = true;
+                tlC = TmaLaunch{(int)(c.m_out / N2), 0, half, pair};
+            }
+        }
+    }
     long long group_index = 0;
     for (long long f0 = 0; f0 < c.nfft; f0 += G, ++group_index) {
         const long long g = std::min(G, c.nfft - f0);
@@ -506,9 +599,14 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
             pa.tw = tw_cols;
             pa.ncols = c.ncols - f0 * cols_per_fft;
             if (c.x_mode == IO_SPEC) return set_error(TB200_BAD_ARG, "internal: IO_SPEC input with forward transform");
-            pa.x = reinterpret_cast<const char*>(c.x) + (size_t)f0 * cols_per_fft * c.ldx * in_esz;
+            if (c.colmap) pa.colmap = c.colmap + f0 * cols_per_fft;
+            else pa.x = reinterpret_cast<const char*>(c.x) + (size_t)f0 * cols_per_fft * c.ldx * in_esz;
             count_launch();
             PassTimer pt(0, s);
+            if (tmaA) {
+                tlA.col0 = (int)(f0 * cols_per_fft);
+                TB_CUDA(launch_colsA_tma<R>(h->log2l1, h->ta, pa, &xmap, tlA, s), "k_colsA_tma");
+            } else
             TB_CUDA(launch_colsA<R>(h->log2l1, h->ta, pa, s), "k_colsA");
         }
         // pass B: rows of the scratch, in place
@@ -520,6 +618,7 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
             pb.x = scratch; pb.x_mode = IO_CPLX; pb.y = scratch; pb.y_mode = IO_CPLX;
             pb.spec_rows = (int)N1;
             pb.scale = (R)1; pb.alpha = mk<R>(1, 0); pb.beta = mk<R>(0, 0); pb.has_beta = 0;
+            pb.colmap = nullptr; pb.col_alpha = nullptr;
             if (!c.do_fwd) {             // inverse only: rows come from a layout-order spectrum
                 pb.x = c.x; pb.x_mode = IO_SPEC; pb.spec = nullptr;
                 if (g != 1 || c.nfft != 1) return set_error(TB200_BAD_ARG, "internal: inverse-only runs one transform");
@@ -538,12 +637,21 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
             pc.nfft = g;
             pc.tw = tw_cols;
             pc.ncols = c.ncols - f0 * cols_per_fft;
-            pc.y = reinterpret_cast<char*>(c.y) + (size_t)f0 * cols_per_fft * c.ldy * out_esz;
+            if (c.colmap) pc.colmap = c.colmap + f0 * cols_per_fft;
+            else {
+                pc.y = reinterpret_cast<char*>(c.y) + (size_t)f0 * cols_per_fft * c.ldy * out_esz;
+                if (c.col_alpha) pc.col_alpha = c.col_alpha + f0 * cols_per_fft * c.col_alpha_stride;   // indexed by user column
+            }
             count_launch();
             PassTimer pt(2, s);
+            if (tmaC) {
+                tlC.col0 = (int)(f0 * cols_per_fft);
+                TB_CUDA(launch_colsC_tma<R>(h->log2l1, h->ta, pc, &ymap, tlC, s), "k_colsC_tma");
+            } else
             TB_CUDA(launch_colsC<R>(h->log2l1, h->ta, pc, s), "k_colsC");
         }
     }
+    if (l2win && !overlap) apply_l2_window(user_stream, nullptr, 0, 1);      // never leave a window on the caller's stream
     if (overlap) {
         for (int i = 0; i < nstr; ++i) {
             TB_CUDA(cudaEventRecord(w->ev_join[i], w->hs[i]), "join");
@@ -741,6 +849,9 @@ int tb200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "krylov_work_bytes")) { g_krylov_work_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "host_chunk_bytes")) { g_host_chunk_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "time_passes")) { g_time_passes = value ? 1 : 0; return TB200_OK; }
+    if (!strcmp(name, "l2_persist_mb")) { g_l2_persist_mb = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 1024); return TB200_OK; }
+    if (!strcmp(name, "prune_half")) { g_prune_half = value ? 1 : 0; return TB200_OK; }
+    if (!strcmp(name, "tma")) { g_tma = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 3); return TB200_OK; }   // bit 0: pass A loads, bit 1: pass C stores
     if (!strcmp(name, "overlap_streams")) { g_overlap_streams = (int)std::min<int64_t>(std::max<int64_t>(value, 0), tb200_fact::MAXS); return TB200_OK; }
     if (!strcmp(name, "l2max_f64")) { g_l2max_f64 = (int)value; return TB200_OK; }
     if (!strcmp(name, "l2max_f32")) { g_l2max_f32 = (int)value; return TB200_OK; }
@@ -828,8 +939,12 @@ int tb200_spectrum_buffer(tb200_handle_t h, void** ptr, int64_t* bytes) {
 }
 
 // ---- mul! --------------------------------------------------------------------------------
+struct ColSel {            // optional column selection / per-column scalars of the batched Krylov drivers (device pointers)
+    const int* colmap = nullptr; const double* col_alpha = nullptr; int col_alpha_stride = 0;
+};
 static int mul_impl(tb200_fact* h, const void* spec, bool is_ldiv, void* y, int64_t ldy, int ydtype, const void* x,
-                    int64_t ldx, int xdtype, int64_t ncols, const double alpha[2], const double beta[2], cudaStream_t s) {
+                    int64_t ldx, int xdtype, int64_t ncols, const double alpha[2], const double beta[2], cudaStream_t s,
+                    const ColSel* sel = nullptr) {
     if (!h) return set_error(TB200_BAD_ARG, "handle is NULL");
     if (!dt_valid(xdtype) || !dt_valid(ydtype)) return set_error(TB200_BAD_ARG, "unknown dtype");
     if (dt_prec(xdtype) != h->prec || dt_prec(ydtype) != h->prec)
@@ -842,6 +957,7 @@ static int mul_impl(tb200_fact* h, const void* spec, bool is_ldiv, void* y, int6
                          (long long)ldy, (long long)ldx, (long long)h->m, (long long)h->n);
     const bool xc = dt_is_cplx(xdtype), yc = dt_is_cplx(ydtype);
     if (h->bluestein) {
+        if (sel && (sel->colmap || sel->col_alpha)) return set_error(TB200_UNSUPPORTED, "internal: column selection on a Bluestein plan");
         if (!yc && (!h->a_real || (!is_ldiv && (xc || (alpha && alpha[1] != 0.0) || (beta && beta[1] != 0.0)))))
             return set_error(TB200_BAD_ARG, "a real y requires a real matrix, real x and real alpha/beta (InexactError in the reference)");
         return bs_run(h, 2, spec, y, ldy, yc, 0, x, ldx, xc, ncols, alpha, beta, s);
@@ -854,6 +970,7 @@ static int mul_impl(tb200_fact* h, const void* spec, bool is_ldiv, void* y, int6
     c.alpha[0] = alpha ? alpha[0] : 1.0; c.alpha[1] = alpha ? alpha[1] : 0.0;
     c.beta[0] = beta ? beta[0] : 0.0; c.beta[1] = beta ? beta[1] : 0.0;
     c.has_beta = (c.beta[0] != 0.0 || c.beta[1] != 0.0);
+    if (sel) { c.colmap = sel->colmap; c.col_alpha = sel->col_alpha; c.col_alpha_stride = sel->col_alpha_stride; }
     if (!yc) {
         if (!is_ldiv && (!h->a_real || xc || c.alpha[1] != 0.0 || c.beta[1] != 0.0))
             return set_error(TB200_BAD_ARG, "a real y requires a real matrix, real x and real alpha/beta (InexactError in the reference)");
@@ -1192,57 +1309,6 @@ int tb200_trench(int dtype, int64_t n, const void* r, void* B, int64_t ldb, doub
 // ---------------------------------------------------------------------------------------
 namespace tb {
 
-typedef std::complex<double> zc;
-
-template <typename T>
-struct KrylovCtx {
-    tb200_fact* A; tb200_fact* M; int dtype; int64_t n; cudaStream_t s;
-    std::shared_ptr<DevBuf> partials, counter, out;
-    double host_out[4];
-
-    int init() {
-        TB_TRY(dev_alloc_on(partials, sizeof(double) * 4 * 4096, "dot partials", s));
-        TB_TRY(dev_alloc_on(counter, 16, "dot counter", s));
-        TB_TRY(dev_alloc_on(out, sizeof(double) * 4, "dot result", s));
-        TB_CUDA(cudaMemsetAsync(counter->p, 0, 16, s), "memset");
-        return TB200_OK;
-    }
-    // host_out[0..1] = dot(a1,b1), [2..3] = dot(a2,b2); synchronises the stream
-    int dots(const T* a1, const T* b1, const T* a2, const T* b2) {
-        unsigned grid = std::min<unsigned>(ew_grid(n), 4096u);
-        k_dot2<T><<<grid, 256, 0, s>>>(a1, b1, a2, b2, n, (double*)partials->p, (unsigned*)counter->p, (double*)out->p);
-        count_launch();
-        TB_CUDA(cudaGetLastError(), "k_dot2");
-        TB_CUDA(cudaMemcpyAsync(host_out, out->p, sizeof(double) * 4, cudaMemcpyDeviceToHost, s), "dot readback");
-        TB_CUDA(cudaStreamSynchronize(s), "dot sync");
-        return TB200_OK;
-    }
-    int mulA(T* y, const T* x, zc alpha, zc beta) {
-        const double a[2] = {alpha.real(), alpha.imag()}, b[2] = {beta.real(), beta.imag()};
-        return mul_impl_fwd(y, x, a, b);
-    }
-    int mul_impl_fwd(T* y, const T* x, const double a[2], const double b[2]);
-    int precond(T* out_v, const T* in_v);   // out = M \ in (may alias)
-};
-
-}  // namespace tb
-
-// mul_impl / tb200_circ_ldiv live in the extern "C" block above; thin forwarders:
-template <typename T>
-int tb::KrylovCtx<T>::mul_impl_fwd(T* y, const T* x, const double a[2], const double b[2]) {
-    return tb200_mul(A, y, n, dtype, x, n, dtype, 1, a, b, (void*)s);
-}
-template <typename T>
-int tb::KrylovCtx<T>::precond(T* out_v, const T* in_v) {
-    if (!M) {
-        if (out_v != in_v) TB_CUDA(cudaMemcpyAsync(out_v, in_v, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, s), "copy");
-        return TB200_OK;
-    }
-    return tb200_circ_ldiv(M, out_v, n, in_v, n, dtype, 1, (void*)s);
-}
-
-namespace tb {
-
 static int check_krylov(tb200_fact* A, tb200_fact* M, int dtype, int64_t n, const void* x, const void* b) {
     if (!A) return set_error(TB200_BAD_ARG, "A is NULL");
     if (!x || !b) return set_error(TB200_BAD_ARG, "x or b is NULL");
@@ -1257,111 +1323,8 @@ static int check_krylov(tb200_fact* A, tb200_fact* M, int dtype, int64_t n, cons
     return TB200_OK;
 }
 
-// IterativeLinearSolvers.cgs, src/iterativeLinearSolvers.jl:99-215
-template <typename T>
-static int cgs_t(tb200_fact* A, tb200_fact* M, T* x, const T* b, int dtype, int64_t n, int max_it, double tol,
-                 double* err_out, int* iter_out, int* flag_out, cudaStream_t s) {
-    KrylovCtx<T> k{A, M, dtype, n, s};
-    TB_TRY(k.init());
-    std::shared_ptr<DevBuf> buf;
-    TB_TRY(dev_alloc_on(buf, sizeof(T) * (size_t)n * 8, "cgs work vectors", s));
-    T* u = (T*)buf->p; T* p = u + n; T* ph = p + n; T* q = ph + n; T* uh = q + n; T* vh = uh + n; T* r = vh + n; T* rt = r + n;
-    TB_CUDA(cudaMemsetAsync(buf->p, 0, sizeof(T) * (size_t)n * 6, s), "memset");       // u,p,ph,q,uh,vh = zeros (:141-146)
-    const unsigned grid = ew_grid(n);
-    int iter = 0, flag = 0;
-    TB_TRY(k.dots(b, b, nullptr, nullptr));
-    double bnrm2 = std::sqrt(k.host_out[0]);                                            // :136
-    if (bnrm2 == 0) bnrm2 = 1.0;
-    TB_CUDA(cudaMemcpyAsync(r, b, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, s), "copy");   // :149
-    TB_TRY(k.mulA(r, x, zc(-1, 0), zc(1, 0)));                                          // :150
-    TB_TRY(k.dots(r, r, nullptr, nullptr));
-    double error = std::sqrt(k.host_out[0]) / bnrm2;                                    // :152
-    zc rho(0, 0), rho1(0, 0);
-    if (error < tol) { *err_out = error; *iter_out = 0; *flag_out = 0; return TB200_OK; }   // :154-156
-    TB_CUDA(cudaMemcpyAsync(rt, r, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, s), "copy");  // :158
-    TB_TRY(k.dots(rt, r, nullptr, nullptr));
-    zc rho_next(k.host_out[0], k.host_out[1]);
-    for (int it = 1; it <= max_it; ++it) {
-        iter = it;
-        rho = rho_next;                                                                 // :163
-        if (rho == zc(0, 0)) break;                                                     // :164-166
-        zc beta(0, 0);
-        if (it > 1) beta = rho / rho1;                                                  // :169
-        k_cgs_dir<T><<<grid, 256, 0, s>>>(u, p, r, q, make_double2(beta.real(), beta.imag()), it == 1, n);   // :168-177
-        count_launch();
-        TB_TRY(k.precond(ph, p));                                                       // :179-180
-        TB_TRY(k.mulA(vh, ph, zc(1, 0), zc(0, 0)));                                     // :182
-        TB_TRY(k.dots(rt, vh, nullptr, nullptr));
-        const zc alpha = rho / zc(k.host_out[0], k.host_out[1]);                        // :184
-        k_cgs_q<T><<<grid, 256, 0, s>>>(q, uh, u, vh, make_double2(alpha.real(), alpha.imag()), n);          // :185-188
-        count_launch();
-        TB_TRY(k.precond(uh, uh));                                                      // :189
-        k_axpy<T><<<grid, 256, 0, s>>>(x, make_double2(alpha.real(), alpha.imag()), uh, n);                  // :192-194
-        count_launch();
-        TB_TRY(k.mulA(r, uh, -alpha, zc(1, 0)));                                        // :196
-        TB_TRY(k.dots(r, r, rt, r));                                                    // norm(r) and the next rho in one sweep
-        error = std::sqrt(k.host_out[0]) / bnrm2;                                       // :198
-        rho_next = zc(k.host_out[2], k.host_out[3]);
-        if (error <= tol) break;                                                        // :199-201
-        rho1 = rho;
-    }
-    if (error <= tol) flag = 0;
-    else if (rho == zc(0, 0)) flag = -1;
-    else flag = 1;
-    *err_out = error; *iter_out = iter; *flag_out = flag;
-    TB_CUDA(cudaStreamSynchronize(s), "cgs sync");
-    return TB200_OK;
-}
-
-// IterativeLinearSolvers.cg, src/iterativeLinearSolvers.jl:9-97.  flag_out = 2 marks the
-// reference's value-less early return (:57-59); the host layer turns it into the same failure.
-template <typename T>
-static int cg_t(tb200_fact* A, tb200_fact* M, T* x, const T* b, int dtype, int64_t n, int max_it, double tol,
-                double* err_out, int* iter_out, int* flag_out, cudaStream_t s) {
-    KrylovCtx<T> k{A, M, dtype, n, s};
-    TB_TRY(k.init());
-    std::shared_ptr<DevBuf> buf;
-    TB_TRY(dev_alloc_on(buf, sizeof(T) * (size_t)n * 4, "cg work vectors", s));
-    T* z = (T*)buf->p; T* q = z + n; T* p = q + n; T* r = p + n;
-    TB_CUDA(cudaMemsetAsync(buf->p, 0, sizeof(T) * (size_t)n * 3, s), "memset");
-    const unsigned grid = ew_grid(n);
-    int iter = 0, flag = 0;
-    TB_TRY(k.dots(b, b, nullptr, nullptr));
-    double bnrm2 = std::sqrt(k.host_out[0]);
-    if (bnrm2 == 0.0) bnrm2 = 1.0;
-    TB_CUDA(cudaMemcpyAsync(r, b, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, s), "copy");
-    TB_TRY(k.mulA(r, x, zc(-1, 0), zc(1, 0)));                                          // :55  r = b - A*x
-    TB_TRY(k.dots(r, r, nullptr, nullptr));
-    double error = std::sqrt(k.host_out[0]) / bnrm2;
-    if (error < tol) { *err_out = error; *iter_out = 0; *flag_out = 2; return TB200_OK; }   // :57-59
-    zc rho1(0, 0);
-    for (int it = 1; it <= max_it; ++it) {
-        iter = it;
-        TB_TRY(k.precond(z, r));                                                        // :64-65
-        TB_TRY(k.dots(r, z, nullptr, nullptr));
-        const zc rho(k.host_out[0], k.host_out[1]);                                     // :67
-        zc beta(0, 0);
-        if (it > 1) beta = rho / rho1;
-        k_cg_dir<T><<<grid, 256, 0, s>>>(p, z, make_double2(beta.real(), beta.imag()), it == 1, n);          // :69-76
-        count_launch();
-        TB_TRY(k.mulA(q, p, zc(1, 0), zc(0, 0)));                                       // :79
-        TB_TRY(k.dots(p, q, nullptr, nullptr));
-        const zc alpha = rho / zc(k.host_out[0], k.host_out[1]);                        // :80
-        k_cg_upd<T><<<grid, 256, 0, s>>>(x, r, p, q, make_double2(alpha.real(), alpha.imag()), n);           // :81-84
-        count_launch();
-        TB_TRY(k.dots(r, r, nullptr, nullptr));
-        error = std::sqrt(k.host_out[0]) / bnrm2;                                       // :86
-        if (error <= tol) break;
-        rho1 = rho;
-    }
-    if (error > tol) flag = 1;
-    *err_out = error; *iter_out = iter; *flag_out = flag;
-    TB_CUDA(cudaStreamSynchronize(s), "cg sync");
-    return TB200_OK;
-}
-
-
-// ---- batched cgs / cg over the columns of B (krylov_batched.cuh) ---------------------------------------------
+// IterativeLinearSolvers.cgs (src/iterativeLinearSolvers.jl:99-215) and cg (:9-97) over the columns of B; one column
+// is the single-vector solver.  krylov_batched.cuh has the kernels and the per-column state machine.
 template <typename T>
 static int krylov_batched_t(bool is_cg, tb200_fact* A, tb200_fact* M, T* X, int64_t ldx, const T* B, int64_t ldb, int dtype,
                             int64_t n, int64_t nrhs, int max_it, double tol, double* err, int* iter, int* flag, cudaStream_t s) {
@@ -1369,116 +1332,157 @@ static int krylov_batched_t(bool is_cg, tb200_fact* A, tb200_fact* M, T* X, int6
     int64_t chunk = std::max<int64_t>(1, g_krylov_work_bytes.load() / (int64_t)(sizeof(T) * (size_t)n * nvec));
     chunk = std::min<int64_t>(std::min<int64_t>(chunk, nrhs), 65535);
     if (chunk > 1 && (chunk & 1)) --chunk;                       // keep real columns paired in the transforms
-    std::shared_ptr<DevBuf> work, stbuf, partials, counters, nact;
+    std::shared_ptr<DevBuf> work, stbuf, partials, counters, nact, cmap;
     TB_TRY(dev_alloc_on(work, sizeof(T) * (size_t)n * (size_t)chunk * nvec, "batched Krylov work vectors", s));
-    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>(128, (n + 2047) / 2048));
+    // CTAs per column of the dot-product sweeps: enough to fill the chip when there are few columns
+    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>(std::max<long long>(128, 2368 / chunk), (n + 2047) / 2048));
     TB_TRY(dev_alloc_on(stbuf, sizeof(KState) * (size_t)chunk, "Krylov state", s));
     TB_TRY(dev_alloc_on(partials, sizeof(double) * 4 * gx * (size_t)chunk, "dot partials", s));
     TB_TRY(dev_alloc_on(counters, sizeof(unsigned) * (size_t)chunk, "dot counters", s));
     TB_TRY(dev_alloc_on(nact, sizeof(int), "active counter", s));
+    TB_TRY(dev_alloc_on(cmap, sizeof(int) * (size_t)chunk, "active column map", s));
     KState* st = (KState*)stbuf->p;
+    int* colmap = (int*)cmap->p;
     std::vector<KState> host_st((size_t)chunk);
     const double one[2] = {1, 0}, zero[2] = {0, 0}, minus[2] = {-1, 0};
     const size_t vsz = (size_t)n * (size_t)chunk;
     T* w = (T*)work->p;
+    // column selection needs the pow2 kernels on both operators (a Bluestein plan runs every column)
+    const bool can_select = !A->bluestein && !(M && M->bluestein);
+    auto finish = [&](int status) {                     // temporaries are stream-ordered: drain before they go
+        cudaStreamSynchronize(s);
+        return status;
+    };
+#define TB_KTRY(expr) do { int st__ = (expr); if (st__ != TB200_OK) return finish(st__); } while (0)
     for (int64_t c0 = 0; c0 < nrhs; c0 += chunk) {
         const int64_t c = std::min(chunk, nrhs - c0);
         T* Xc = X + c0 * ldx;
         const T* Bc = B + c0 * ldb;
-        const dim3 gdot(gx, (unsigned)c), gew((unsigned)std::max<long long>(1, std::min<long long>((n + 1023) / 1024, 2048)), (unsigned)c);
+        const unsigned gxe = (unsigned)std::max<long long>(1, std::min<long long>((n + 1023) / 1024, 2048));
         const unsigned gs = (unsigned)((c + 127) / 128);
-        int h_active = 0;
-        auto dots = [&](const T* a1, const T* b1, long long ld1, const T* a2, const T* b2, int only_active) -> int {
-            k_bdot2<T><<<gdot, 256, 0, s>>>(a1, b1, ld1, a2, b2, n, n, (double*)partials->p, (unsigned*)counters->p, st, only_active);
+        int h_active = 0;            // columns still iterating, as last read from the device (never below the true count)
+        const int* cm = nullptr;     // column map handed to the kernels (NULL while every column is live)
+        auto dots = [&](const T* a1, const T* b1, long long ld1, const T* a2, const T* b2, int only_active, int ncol) -> int {
+            k_bdot2<T><<<dim3(gx, (unsigned)ncol), 256, 0, s>>>(a1, b1, ld1, a2, b2, n, n, (double*)partials->p, (unsigned*)counters->p,
+                                                              st, only_active, only_active ? cm : nullptr);
             count_launch();
             return cuda_status(cudaGetLastError(), "k_bdot2");
         };
-        auto step = [&](int which, int it, bool count) -> int {
-            if (count) TB_CUDA(cudaMemsetAsync(nact->p, 0, sizeof(int), s), "memset");
-            k_kstep<<<gs, 128, 0, s>>>(st, (int)c, which, it, max_it, tol, (int*)nact->p);
+        auto step = [&](int which, int it) -> int {
+            k_kstep<<<gs, 128, 0, s>>>(st, (int)c, which, it, max_it, tol);
             count_launch();
-            TB_CUDA(cudaGetLastError(), "k_kstep");
-            if (count) {
+            return cuda_status(cudaGetLastError(), "k_kstep");
+        };
+        // partition the columns and (optionally) read the live count back
+        auto compact = [&](bool readback) -> int {
+            k_compact<<<1, 1024, 0, s>>>(st, (int)c, colmap, (int*)nact->p);
+            count_launch();
+            TB_CUDA(cudaGetLastError(), "k_compact");
+            if (readback) {
                 TB_CUDA(cudaMemcpyAsync(&h_active, nact->p, sizeof(int), cudaMemcpyDeviceToHost, s), "active readback");
                 TB_CUDA(cudaStreamSynchronize(s), "Krylov sync");
+                cm = (can_select && h_active < c) ? colmap : nullptr;
             }
             return TB200_OK;
         };
-        auto mulA = [&](T* y, const T* x, int64_t ldxx, const double* a, const double* b) -> int {
-            return tb200_mul(A, y, n, dtype, x, ldxx, dtype, c, a, b, (void*)s);
+        auto mulA = [&](T* y, const T* x, int64_t ldxx, int64_t ncol, const double* a, const double* b, bool all, bool per_col_alpha) -> int {
+            ColSel sel;
+            if (!all) sel.colmap = cm;
+            if (per_col_alpha) { sel.col_alpha = &st[0].alpha[0]; sel.col_alpha_stride = (int)(sizeof(KState) / sizeof(double)); }
+            return mul_impl(A, A->spec->p, false, y, n, dtype, x, ldxx, dtype, (all || !cm) ? c : ncol, a, b, s, &sel);
         };
-        auto precond = [&](T* out_v, const T* in_v) -> int {
+        auto precond = [&](T* out_v, const T* in_v, int64_t ncol) -> int {
             if (!M) {
                 if (out_v != in_v) TB_CUDA(cudaMemcpyAsync(out_v, in_v, sizeof(T) * (size_t)n * (size_t)c, cudaMemcpyDeviceToDevice, s), "copy");
                 return TB200_OK;
             }
-            return tb200_circ_ldiv(M, out_v, n, in_v, n, dtype, c, (void*)s);
+            TB_TRY(ensure_inv_spec(M, s));
+            ColSel sel;
+            sel.colmap = cm;
+            return mul_impl(M, M->inv_spec->p, true, out_v, n, dtype, in_v, n, dtype, cm ? ncol : c, one, zero, s, &sel);
         };
-        TB_CUDA(cudaMemsetAsync(counters->p, 0, sizeof(unsigned) * (size_t)c, s), "memset");
-        TB_CUDA(cudaMemsetAsync(work->p, 0, sizeof(T) * vsz * nvec, s), "memset");          // :141-146 zeros
-        TB_TRY(dots(Bc, Bc, ldb, nullptr, nullptr, 0));
-        TB_TRY(step(KS_BNRM, 0, false));
+        // small problems are launch-bound: read the live count every third iteration only (stale counts are safe, see k_compact)
+        auto sync_now = [&](int it) { return (long long)n * std::max(h_active, 1) >= (1ll << 19) || it % 3 == 0 || it == max_it; };
+        TB_KTRY(cuda_status(cudaMemsetAsync(counters->p, 0, sizeof(unsigned) * (size_t)c, s), "memset"));
+        TB_KTRY(cuda_status(cudaMemsetAsync(work->p, 0, sizeof(T) * vsz * nvec, s), "memset"));          // :141-146 zeros
+        TB_KTRY(dots(Bc, Bc, ldb, nullptr, nullptr, 0, (int)c));
+        TB_KTRY(step(KS_BNRM, 0));
         if (!is_cg) {
             T* u = w; T* p = u + vsz; T* ph = p + vsz; T* q = ph + vsz; T* uh = q + vsz; T* vh = uh + vsz; T* r = vh + vsz; T* rt = r + vsz;
-            TB_CUDA(cudaMemcpy2DAsync(r, sizeof(T) * (size_t)n, Bc, sizeof(T) * (size_t)ldb, sizeof(T) * (size_t)n, (size_t)c,
-                                      cudaMemcpyDeviceToDevice, s), "copy");                   // :149
-            TB_TRY(mulA(r, Xc, ldx, minus, one));                                              // :150
-            TB_TRY(dots(r, r, n, nullptr, nullptr, 0));
-            TB_TRY(step(KS_INIT_CGS, 0, true));
+            TB_KTRY(cuda_status(cudaMemcpy2DAsync(r, sizeof(T) * (size_t)n, Bc, sizeof(T) * (size_t)ldb, sizeof(T) * (size_t)n, (size_t)c,
+                                                  cudaMemcpyDeviceToDevice, s), "copy"));                   // :149
+            TB_KTRY(mulA(r, Xc, ldx, c, minus, one, true, false));                                          // :150
+            TB_KTRY(dots(r, r, n, nullptr, nullptr, 0, (int)c));
+            TB_KTRY(step(KS_INIT_CGS, 0));
+            TB_KTRY(compact(true));
             if (h_active > 0) {
-                TB_CUDA(cudaMemcpyAsync(rt, r, sizeof(T) * (size_t)n * (size_t)c, cudaMemcpyDeviceToDevice, s), "copy");   // :158
-                TB_TRY(dots(rt, r, n, nullptr, nullptr, 1));
-                TB_TRY(step(KS_RHO0, 0, false));
+                TB_KTRY(cuda_status(cudaMemcpyAsync(rt, r, sizeof(T) * (size_t)n * (size_t)c, cudaMemcpyDeviceToDevice, s), "copy"));   // :158
+                TB_KTRY(dots(rt, r, n, nullptr, nullptr, 1, cm ? h_active : (int)c));
+                TB_KTRY(step(KS_RHO0, 0));
                 for (int it = 1; it <= max_it && h_active > 0; ++it) {
-                    TB_TRY(step(KS_CGS_BEGIN, it, false));
-                    k_bcgs_dir<T><<<gew, 256, 0, s>>>(u, p, r, q, st, it == 1, n, n);          // :168-177
+                    const int na = cm ? h_active : (int)c;
+                    const dim3 gew(gxe, (unsigned)na);
+                    TB_KTRY(step(KS_CGS_BEGIN, it));
+                    k_bcgs_dir<T><<<gew, 256, 0, s>>>(u, p, r, q, st, it == 1, n, n, cm);                   // :168-177
                     count_launch();
-                    TB_TRY(precond(ph, p));                                                    // :179-180
-                    TB_TRY(mulA(vh, ph, n, one, zero));                                        // :182
-                    TB_TRY(dots(rt, vh, n, nullptr, nullptr, 1));
-                    TB_TRY(step(KS_CGS_ALPHA, it, false));                                     // :184
-                    k_bcgs_q<T><<<gew, 256, 0, s>>>(q, uh, u, vh, st, n, n);                   // :185-188
+                    TB_KTRY(precond(ph, p, na));                                                            // :179-180
+                    TB_KTRY(mulA(vh, ph, n, na, one, zero, false, false));                                  // :182
+                    TB_KTRY(dots(rt, vh, n, nullptr, nullptr, 1, na));
+                    TB_KTRY(step(KS_CGS_ALPHA, it));                                                        // :184
+                    k_bcgs_q<T><<<gew, 256, 0, s>>>(q, uh, u, vh, st, n, n, cm);                            // :185-188
                     count_launch();
-                    TB_TRY(precond(uh, uh));                                                   // :189
-                    TB_TRY(mulA(vh, uh, n, one, zero));                                        // A*uh (vh is free again)
-                    k_bxr<T><<<gew, 256, 0, s>>>(Xc, ldx, r, uh, vh, st, n, n);                // :192-196
-                    count_launch();
-                    TB_TRY(dots(r, r, n, rt, r, 1));
-                    TB_TRY(step(KS_CGS_END, it, true));                                        // :198-201
+                    TB_KTRY(precond(uh, uh, na));                                                           // :189
+                    if (!A->bluestein) {
+                        k_bx<T><<<gew, 256, 0, s>>>(Xc, ldx, uh, st, n, n, cm);                             // :192-194
+                        count_launch();
+                        TB_KTRY(mulA(r, uh, n, na, minus, one, false, true));                               // :196  r -= alpha_j * A * uh
+                    } else {                                                                                // chirp-z plan: unfused
+                        TB_KTRY(mulA(vh, uh, n, na, one, zero, false, false));
+                        k_bxr<T><<<gew, 256, 0, s>>>(Xc, ldx, r, uh, vh, st, n, n, cm);
+                        count_launch();
+                    }
+                    TB_KTRY(dots(r, r, n, rt, r, 1, na));
+                    TB_KTRY(step(KS_CGS_END, it));                                                          // :198-201
+                    TB_KTRY(compact(sync_now(it)));
                 }
             }
         } else {
             T* z = w; T* q = z + vsz; T* p = q + vsz; T* r = p + vsz;
-            TB_CUDA(cudaMemcpy2DAsync(r, sizeof(T) * (size_t)n, Bc, sizeof(T) * (size_t)ldb, sizeof(T) * (size_t)n, (size_t)c,
-                                      cudaMemcpyDeviceToDevice, s), "copy");
-            TB_TRY(mulA(r, Xc, ldx, minus, one));                                              // :55
-            TB_TRY(dots(r, r, n, nullptr, nullptr, 0));
-            TB_TRY(step(KS_INIT_CG, 0, true));
+            TB_KTRY(cuda_status(cudaMemcpy2DAsync(r, sizeof(T) * (size_t)n, Bc, sizeof(T) * (size_t)ldb, sizeof(T) * (size_t)n, (size_t)c,
+                                                  cudaMemcpyDeviceToDevice, s), "copy"));
+            TB_KTRY(mulA(r, Xc, ldx, c, minus, one, true, false));                                          // :55
+            TB_KTRY(dots(r, r, n, nullptr, nullptr, 0, (int)c));
+            TB_KTRY(step(KS_INIT_CG, 0));
+            TB_KTRY(compact(true));
             for (int it = 1; it <= max_it && h_active > 0; ++it) {
-                TB_TRY(precond(z, r));                                                         // :64-65
-                TB_TRY(dots(r, z, n, nullptr, nullptr, 1));
-                TB_TRY(step(KS_CG_BEGIN, it, false));                                          // :67-68
-                k_bcg_dir<T><<<gew, 256, 0, s>>>(p, z, st, it == 1, n, n);                     // :69-76
+                const int na = cm ? h_active : (int)c;
+                const dim3 gew(gxe, (unsigned)na);
+                TB_KTRY(precond(z, r, na));                                                                 // :64-65
+                TB_KTRY(dots(r, z, n, nullptr, nullptr, 1, na));
+                TB_KTRY(step(KS_CG_BEGIN, it));                                                             // :67-68
+                k_bcg_dir<T><<<gew, 256, 0, s>>>(p, z, st, it == 1, n, n, cm);                              // :69-76
                 count_launch();
-                TB_TRY(mulA(q, p, n, one, zero));                                              // :79
-                TB_TRY(dots(p, q, n, nullptr, nullptr, 1));
-                TB_TRY(step(KS_CG_ALPHA, it, false));                                          // :80
-                k_bxr<T><<<gew, 256, 0, s>>>(Xc, ldx, r, p, q, st, n, n);                      // :81-84
+                TB_KTRY(mulA(q, p, n, na, one, zero, false, false));                                        // :79
+                TB_KTRY(dots(p, q, n, nullptr, nullptr, 1, na));
+                TB_KTRY(step(KS_CG_ALPHA, it));                                                             // :80
+                k_bxr<T><<<gew, 256, 0, s>>>(Xc, ldx, r, p, q, st, n, n, cm);                               // :81-84
                 count_launch();
-                TB_TRY(dots(r, r, n, nullptr, nullptr, 1));
-                TB_TRY(step(KS_CG_END, it, true));                                             // :86-88
+                TB_KTRY(dots(r, r, n, nullptr, nullptr, 1, na));
+                TB_KTRY(step(KS_CG_END, it));                                                               // :86-88
+                TB_KTRY(compact(sync_now(it)));
             }
         }
-        TB_CUDA(cudaGetLastError(), "batched Krylov kernels");
-        TB_CUDA(cudaMemcpyAsync(host_st.data(), st, sizeof(KState) * (size_t)c, cudaMemcpyDeviceToHost, s), "state readback");
-        TB_CUDA(cudaStreamSynchronize(s), "Krylov sync");
+        TB_KTRY(cuda_status(cudaGetLastError(), "batched Krylov kernels"));
+        TB_KTRY(cuda_status(cudaMemcpyAsync(host_st.data(), st, sizeof(KState) * (size_t)c, cudaMemcpyDeviceToHost, s), "state readback"));
+        TB_KTRY(cuda_status(cudaStreamSynchronize(s), "Krylov sync"));
         for (int64_t j = 0; j < c; ++j) {
             if (err) err[c0 + j] = host_st[(size_t)j].error;
             if (iter) iter[c0 + j] = host_st[(size_t)j].iter;
             if (flag) flag[c0 + j] = host_st[(size_t)j].flag;
         }
     }
-    return TB200_OK;
+#undef TB_KTRY
+    return finish(TB200_OK);
 }
 
 static int krylov_batched(bool is_cg, tb200_fact* A, tb200_fact* M, void* X, int64_t ldx, const void* B, int64_t ldb, int dtype,
@@ -1511,37 +1515,15 @@ int tb200_cg_batched(tb200_handle_t A, tb200_handle_t M, void* X, int64_t ldx, c
     return krylov_batched(true, A, M, X, ldx, B, ldb, dtype, n, nrhs, max_it, tol, err, iter, flag, stream);
 }
 
+// single-vector solvers = the one-column case of the batched drivers (scalars stay on the device)
 int tb200_cgs(tb200_handle_t A, tb200_handle_t M, void* x, const void* b, int dtype, int64_t n, int max_it, double tol,
               double* err, int* iter, int* flag, void* stream) {
-    DeviceGuard dev_guard(A);
-    TB_TRY(check_krylov(A, M, dtype, n, x, b));
-    double e = 0; int it = 0, fl = 0, st;
-    cudaStream_t s = (cudaStream_t)stream;
-    switch (dtype) {
-    case TB200_F32: st = cgs_t<float>(A, M, (float*)x, (const float*)b, dtype, n, max_it, tol, &e, &it, &fl, s); break;
-    case TB200_F64: st = cgs_t<double>(A, M, (double*)x, (const double*)b, dtype, n, max_it, tol, &e, &it, &fl, s); break;
-    case TB200_C32: st = cgs_t<float2>(A, M, (float2*)x, (const float2*)b, dtype, n, max_it, tol, &e, &it, &fl, s); break;
-    default: st = cgs_t<double2>(A, M, (double2*)x, (const double2*)b, dtype, n, max_it, tol, &e, &it, &fl, s); break;
-    }
-    if (err) *err = e;
-    if (iter) *iter = it;
-    if (flag) *flag = fl;
-    return st;
+    return krylov_batched(false, A, M, x, n, b, n, dtype, n, 1, max_it, tol, err, iter, flag, stream);
 }
 
 int tb200_cg(tb200_handle_t A, tb200_handle_t M, void* x, const void* b, int dtype, int64_t n, int max_it, double tol,
              double* err, int* iter, int* flag, void* stream) {
-    DeviceGuard dev_guard(A);
-    TB_TRY(check_krylov(A, M, dtype, n, x, b));
-    if (dt_is_cplx(dtype)) return set_error(TB200_BAD_ARG, "cg is defined for real (BlasReal) element types only");
-    double e = 0; int it = 0, fl = 0, st;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == TB200_F32) st = cg_t<float>(A, M, (float*)x, (const float*)b, dtype, n, max_it, tol, &e, &it, &fl, s);
-    else st = cg_t<double>(A, M, (double*)x, (const double*)b, dtype, n, max_it, tol, &e, &it, &fl, s);
-    if (err) *err = e;
-    if (iter) *iter = it;
-    if (flag) *flag = fl;
-    return st;
+    return krylov_batched(true, A, M, x, n, b, n, dtype, n, 1, max_it, tol, err, iter, flag, stream);
 }
 
 }  // extern "C"

@@ -111,6 +111,26 @@ __device__ __forceinline__ void dif_regs(cx<R>* a) {
         }
     }
 }
+// Same with a[RAD/2 .. RAD) == 0 on entry (the zero padding of a circulant embedding, src/linearalgebra.jl:57-62):
+// the first butterfly level degenerates to a[i + RAD/2] = a[i] * w^i and costs no additions.
+template <typename R, int RAD>
+__device__ __forceinline__ void dif_regs_halfzero(cx<R>* a) {
+    static_assert(RAD == 16, "half-zero variant is written for radix-16 threads");
+#pragma unroll
+    for (int i = 0; i < RAD / 2; ++i) a[i + RAD / 2] = mul_w16<R, false>(a[i], i);
+#pragma unroll
+    for (int h = RAD / 4; h >= 1; h >>= 1) {
+#pragma unroll
+        for (int blk = 0; blk < RAD; blk += 2 * h) {
+#pragma unroll
+            for (int i = 0; i < h; ++i) {
+                cx<R> u = a[blk + i], v = a[blk + i + h];
+                a[blk + i] = cadd(u, v);
+                a[blk + i + h] = mul_w16<R, false>(csub(u, v), i * (8 / h));
+            }
+        }
+    }
+}
 // Mirror: a[brev(c)] = X[c] in -> natural out, conjugate twiddles (unnormalised inverse).
 template <typename R, int RAD>
 __device__ __forceinline__ void dit_regs(cx<R>* a) {
@@ -137,6 +157,7 @@ template <> __host__ __device__ constexpr int swz_f<double>(int i) { return ((i 
 template <> __host__ __device__ constexpr int swz_f<float>(int i) { return (i >> 4) & 15; }
 
 template <typename R> struct RowMap {       // one FFT contiguous in shared memory
+    static constexpr int TSHIFT = 0;        // FFT thread t sits at bit 0 of the CTA thread index
     __device__ __forceinline__ int pre(int base) const { return base ^ swz_f<R>(base); }
     __device__ __forceinline__ int at(int pre_, int off) const {
         constexpr int FIELD = sizeof(R) == 8 ? 7 : 15;     // bits the swizzle may flip
@@ -144,6 +165,7 @@ template <typename R> struct RowMap {       // one FFT contiguous in shared memo
     }
 };
 template <int TA> struct ColMap {           // TA FFTs interleaved element-wise
+    static constexpr int TSHIFT = ilog2c(TA);    // thread index = t * TA + q
     int q;
     __device__ __forceinline__ int pre(int base) const { return base * TA + q; }
     __device__ __forceinline__ int at(int pre_, int off) const { return pre_ + off * TA; }
@@ -200,6 +222,17 @@ __device__ __forceinline__ float ld_stream(const float* p) {
 #define TB_SM_LOAD(dst, src) dst = src
 #define TB_SM_STORE(dst, src) dst = src
 
+// Barrier between the stores of one stage and the loads of the next.  An element's owner is its index with the
+// stage's digit removed, so the threads that exchange data differ only in bits [lo, lo + LOGE) of t, lo = the smaller
+// of the two strides' log2 (forward: the next stage's, inverse: the storing stage's).  When that field (shifted by the map's thread
+// layout) lies inside the lane index, the exchange never leaves a warp and __syncwarp is enough -- two of the four
+// exchanges of the 4096-point row pass.
+template <int LOGE, int TSHIFT>
+__device__ __forceinline__ void exchange_barrier(int lo) {
+    if (lo + LOGE + TSHIFT <= 5) __syncwarp();
+    else __syncthreads();
+}
+
 // One L-point FFT held by NT threads (t = 0..NT-1), E = 2^LE complex registers each.
 template <typename R, int LOG2L, int LE = le_of<R>()>
 struct SlotFFT {
@@ -230,7 +263,8 @@ struct SlotFFT {
 
     // On entry a[c] = x[t + c*NT] (or, with FROM_SMEM, the natural-order input already sits in shared
     // memory at sm[map(idx)]).  On exit register i holds X[freq_of_pos(pos_of_reg(i,t))].
-    template <class Map, bool FROM_SMEM = false>
+    // HALF_IN: a[E/2 .. E) are known zeros (upper half of the input is padding) and need not be initialised.
+    template <class Map, bool FROM_SMEM = false, bool HALF_IN = false>
     __device__ __forceinline__ static void forward(cx<R>* a, int t, cx<R>* sm, Map map,
                                                    const cx<R>* __restrict__ tw) {
 #pragma unroll
@@ -243,7 +277,12 @@ struct SlotFFT {
 #pragma unroll
                 for (int c = 0; c < E; ++c) TB_SM_LOAD(a[c], sm[map.at(pre, c << ls)]);
             }
-            dif_regs<R, E>(a);
+            if constexpr (HALF_IN && !FROM_SMEM && E == 16) {
+                if (k == 0) dif_regs_halfzero<R, E>(a);
+                else dif_regs<R, E>(a);
+            } else {
+                dif_regs<R, E>(a);
+            }
             if (ls > 0) {
                 cx<R> w[E];
                 stage_twiddles_of_thread<R, E>(tw + stage_tw_off(LOG2L, k, LOGE), s, r, w);
@@ -254,7 +293,8 @@ struct SlotFFT {
             if (!last) {
 #pragma unroll
                 for (int c = 0; c < E; ++c) TB_SM_STORE(sm[map.at(pre, c << ls)], a[brev(c, LOGE)]);
-                __syncthreads();
+                if (k + 1 < NFULL) exchange_barrier<LOGE, Map::TSHIFT>(ls - LOGE);
+                else __syncthreads();
             }
         }
         if (REM > 0) {
@@ -305,7 +345,7 @@ struct SlotFFT {
             if (k > 0) {
 #pragma unroll
                 for (int c = 0; c < E; ++c) TB_SM_STORE(sm[map.at(pre, c << ls)], a[c]);
-                __syncthreads();
+                exchange_barrier<LOGE, Map::TSHIFT>(ls);     // writer and reader of an element differ in bits [ls, ls+LOGE) of t
             }
         }
     }

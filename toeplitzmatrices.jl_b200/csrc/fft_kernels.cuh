@@ -39,6 +39,12 @@ struct ConvArgs {
     const cx<R>* tw_lo; const cx<R>* tw_hi; int tw_hb;   // w_Np^m = lo[m & mask] * hi[m >> hb]
     const cx<R>* tw_g;        // [E][N2]: w_Np^(delta_i * j2), delta_i = frequency offset of register i (thread-independent);
                               // the kernels read rows i = 2^b only and build the rest as subset products
+    // column indirection (batched Krylov solvers: only the columns still iterating are transformed): user column of
+    // logical column j is colmap[j]; NULL = identity.  x and y use the same map.
+    const int* colmap;
+    // per-column device scalars (batched Krylov: r -= alpha_j * A * uh fused into the epilogue): the effective alpha of
+    // user column j is alpha * (col_alpha[j*stride], col_alpha[j*stride + 1]); NULL = none
+    const double* col_alpha; int col_alpha_stride;
 };
 
 // Inter-level twiddles of one thread (fixed column j2): w^(k1(i) j2) = w^(kbase(t) j2) * w^(delta_i j2).
@@ -54,11 +60,13 @@ struct InView {
     __device__ __forceinline__ InView(const ConvArgs<R>& p, long long f) {
         mode = p.x_mode; n_in = (int)p.n_in; rev = p.reverse_x;
         re = nullptr; im = nullptr; c = nullptr;
-        if (mode == IO_CPLX) c = reinterpret_cast<const cx<R>*>(p.x) + f * p.ldx;
-        else if (mode == IO_REAL) re = reinterpret_cast<const R*>(p.x) + f * p.ldx;
+        const int* cm = p.colmap;
+        if (mode == IO_CPLX) c = reinterpret_cast<const cx<R>*>(p.x) + (cm ? (long long)cm[f] : f) * p.ldx;
+        else if (mode == IO_REAL) re = reinterpret_cast<const R*>(p.x) + (cm ? (long long)cm[f] : f) * p.ldx;
         else if (mode == IO_PAIR) {
-            re = reinterpret_cast<const R*>(p.x) + (2 * f) * p.ldx;
-            im = (2 * f + 1 < p.ncols) ? re + p.ldx : nullptr;
+            const R* base = reinterpret_cast<const R*>(p.x);
+            re = base + (cm ? (long long)cm[2 * f] : 2 * f) * p.ldx;
+            im = (2 * f + 1 < p.ncols) ? base + (cm ? (long long)cm[2 * f + 1] : 2 * f + 1) * p.ldx : nullptr;
         }
     }
     __device__ __forceinline__ cx<R> load(int idx) const {
@@ -73,18 +81,32 @@ struct InView {
 
 template <typename R>
 struct OutView {
-    R* re; R* im; cx<R>* c; int mode; int m_out; int has_beta; cx<R> as, beta; bool unit;
+    R* re; R* im; cx<R>* c; int mode; int m_out; int has_beta; cx<R> as, beta; R as_im; bool unit;
     __device__ __forceinline__ OutView(const ConvArgs<R>& p, long long f) {
         mode = p.y_mode; m_out = (int)p.m_out; has_beta = p.has_beta; beta = p.beta;
         as = mk<R>(p.alpha.x * p.scale, p.alpha.y * p.scale);       // alpha/N' folded into one factor
-        unit = !has_beta && as.x == (R)1 && as.y == (R)0;           // pass B of the two-level transform: plain stores
         re = nullptr; im = nullptr; c = nullptr;
-        if (mode == IO_CPLX) c = reinterpret_cast<cx<R>*>(p.y) + f * p.ldy;
-        else if (mode == IO_REAL) re = reinterpret_cast<R*>(p.y) + f * p.ldy;
+        const int* cm = p.colmap;
+        long long j0 = 0, j1 = 0;
+        if (mode == IO_CPLX) { j0 = cm ? (long long)cm[f] : f; c = reinterpret_cast<cx<R>*>(p.y) + j0 * p.ldy; }
+        else if (mode == IO_REAL) { j0 = cm ? (long long)cm[f] : f; re = reinterpret_cast<R*>(p.y) + j0 * p.ldy; }
         else if (mode == IO_PAIR) {
-            re = reinterpret_cast<R*>(p.y) + (2 * f) * p.ldy;
-            im = (2 * f + 1 < p.ncols) ? re + p.ldy : nullptr;
+            R* base = reinterpret_cast<R*>(p.y);
+            j0 = cm ? (long long)cm[2 * f] : 2 * f;
+            re = base + j0 * p.ldy;
+            if (2 * f + 1 < p.ncols) { j1 = cm ? (long long)cm[2 * f + 1] : 2 * f + 1; im = base + j1 * p.ldy; }
         }
+        as_im = as.x;
+        if (p.col_alpha) {                                          // per-column device scalar times alpha/N'
+            const double* a0 = p.col_alpha + j0 * p.col_alpha_stride;
+            const cx<R> s0 = mk<R>((R)a0[0], (R)a0[1]);
+            if (mode == IO_CPLX) as = cmul(as, s0);
+            else {
+                if (im) as_im = as.x * (R)p.col_alpha[j1 * p.col_alpha_stride];
+                as.x *= s0.x;
+            }
+        }
+        unit = !has_beta && as.x == (R)1 && as.y == (R)0 && !p.col_alpha;   // pass B of the two-level transform: plain stores
     }
     __device__ __forceinline__ void store(int idx, cx<R> v) const {
         if (idx >= m_out) return;
@@ -98,7 +120,7 @@ struct OutView {
             if (has_beta) o0 = fma(beta.x, re[idx], o0);
             re[idx] = o0;
             if (im) {
-                R o1 = as.x * v.y;
+                R o1 = as_im * v.y;
                 if (has_beta) o1 = fma(beta.x, im[idx], o1);
                 im[idx] = o1;
             }
@@ -187,8 +209,9 @@ __device__ __forceinline__ void level_twiddles(const ConvArgs<R>& p, int t, int 
     }
 }
 
-// grid.x = (N2/TA) * nfft ; block = TA * NT1
-template <typename R, int LOG2L1, int TA>
+// grid.x = (N2/TA) * nfft ; block = TA * NT1.  HALF: the input occupies at most the first half of the embedding
+// (n <= N'/2, every Toeplitz/Hankel product), so rows >= N1/2 are padding: not loaded, first butterfly level pruned.
+template <typename R, int LOG2L1, int TA, bool HALF>
 __global__ void __launch_bounds__((1 << (LOG2L1 - le_of<R>())) * TA, min_ctas<R>((1 << (LOG2L1 - le_of<R>())) * TA, (int)sizeof(cx<R>) * (1 << LOG2L1) * TA))
 k_colsA(const ConvArgs<R> p) {
     using F = SlotFFT<R, LOG2L1>;
@@ -205,9 +228,9 @@ k_colsA(const ConvArgs<R> p) {
     {
         const InView<R> in(p, f);
 #pragma unroll
-        for (int c = 0; c < E; ++c) a[c] = in.load(((t + c * NT) << l2) + j2);
+        for (int c = 0; c < (HALF ? E / 2 : E); ++c) a[c] = in.load(((t + c * NT) << l2) + j2);
     }
-    F::forward(a, t, sm, map, p.tw);
+    F::template forward<ColMap<TA>, false, HALF>(a, t, sm, map, p.tw);
     cx<R>* out = p.scratch + (f << (l2 + LOG2L1)) + j2;
     cx<R> w[E];
     level_twiddles<R, F>(p, t, j2, w);
@@ -215,7 +238,9 @@ k_colsA(const ConvArgs<R> p) {
     for (int i = 0; i < E; ++i) out[(long long)F::pos_of_reg(i, t) << l2] = cmul(a[i], w[i]);
 }
 
-template <typename R, int LOG2L1, int TA>
+// HALF: only the first half of the embedding is wanted (m <= N'/2): outputs j >= E/2 are never stored and the
+// compiler drops the second half of the last butterfly level.
+template <typename R, int LOG2L1, int TA, bool HALF>
 __global__ void __launch_bounds__((1 << (LOG2L1 - le_of<R>())) * TA, min_ctas<R>((1 << (LOG2L1 - le_of<R>())) * TA, (int)sizeof(cx<R>) * (1 << LOG2L1) * TA))
 k_colsC(const ConvArgs<R> p) {
     using F = SlotFFT<R, LOG2L1>;
@@ -239,7 +264,7 @@ k_colsC(const ConvArgs<R> p) {
     F::inverse(a, t, sm, map, p.tw);
     const OutView<R> out(p, f);
 #pragma unroll
-    for (int j = 0; j < E; ++j) out.store(((t + j * NT) << l2) + j2, a[j]);
+    for (int j = 0; j < (HALF ? E / 2 : E); ++j) out.store(((t + j * NT) << l2) + j2, a[j]);
 }
 
 }  // namespace tb

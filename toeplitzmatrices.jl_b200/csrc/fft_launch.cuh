@@ -36,11 +36,25 @@ cudaError_t launch_rows_one(const ConvArgs<R>& a, int num_sms, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// pruned variants (half of the embedding is padding) exist for radix-16 threads with at least one full stage
+extern int g_prune_half;
+template <typename R, int LOG2L1, int TA, bool LAST, bool HALF>
+cudaError_t launch_cols_v(const ConvArgs<R>& a, cudaStream_t s);
+
 template <typename R, int LOG2L1, int TA, bool LAST>
 cudaError_t launch_cols_one(const ConvArgs<R>& a, cudaStream_t s) {
+    const long long half = 1LL << (a.log2n2 + LOG2L1 - 1);
+    const bool can_half = g_prune_half && le_of<R>() == 4 && LOG2L1 >= 4 &&
+                          (LAST ? (a.m_out <= half) : (a.n_in <= half && a.x_mode != IO_SPEC));
+    if (can_half) return launch_cols_v<R, LOG2L1, TA, LAST, true>(a, s);
+    return launch_cols_v<R, LOG2L1, TA, LAST, false>(a, s);
+}
+
+template <typename R, int LOG2L1, int TA, bool LAST, bool HALF>
+cudaError_t launch_cols_v(const ConvArgs<R>& a, cudaStream_t s) {
     constexpr int threads = (1 << (LOG2L1 - le_of<R>())) * TA;
     constexpr size_t smem = sizeof(cx<R>) * (size_t)(1 << LOG2L1) * TA;
-    auto kern = LAST ? k_colsC<R, LOG2L1, TA> : k_colsA<R, LOG2L1, TA>;
+    auto kern = LAST ? k_colsC<R, LOG2L1, TA, HALF> : k_colsA<R, LOG2L1, TA, HALF>;
     static bool configured[64] = {};          // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -54,5 +68,11 @@ cudaError_t launch_cols_one(const ConvArgs<R>& a, cudaStream_t s) {
     kern<<<(unsigned)grid, threads, smem, s>>>(a);
     return cudaGetLastError();
 }
+
+// ---- TMA-staged strided passes (tma_cols.cuh), instantiated for the plans of the BASELINE configs ----------------
+struct TmaLaunch { int rows; int col0; bool half; bool pair; };
+template <typename R> bool cols_tma_supported(int log2l1, int ta, bool pair);
+template <typename R> cudaError_t launch_colsA_tma(int log2l1, int ta, const ConvArgs<R>& a, const void* tensor_map, const TmaLaunch& t, cudaStream_t s);
+template <typename R> cudaError_t launch_colsC_tma(int log2l1, int ta, const ConvArgs<R>& a, const void* tensor_map, const TmaLaunch& t, cudaStream_t s);
 
 }  // namespace tb

@@ -2,8 +2,11 @@
 // solves (/root/reference/src/linearalgebra.jl:102-110 calling :133-136, :152, :399-402).  Here all columns of a chunk
 // iterate together: the structured products and preconditioner solves run on the batched FFT path (two real columns
 // per transform), the vector updates are single sweeps over the whole chunk, and every per-column scalar
-// (rho, alpha, beta, error, flags) lives on the device -- one host synchronisation per iteration (the number of
-// columns still iterating) instead of two per column.  Per column the arithmetic is the reference's
+// (rho, alpha, beta, error, flags) lives on the device.  After every iteration `k_compact` partitions the column indices
+// into "still iterating" | "frozen" (stable), and the next iteration's products, preconditioner solves and sweeps run on
+// the first group only (column indirection in the FFT kernels, fft_kernels.cuh) -- a straggler column costs one column's
+// work, not the whole chunk's.  The host reads one integer (columns still iterating) per iteration, or every third
+// iteration for small problems; single-vector cgs / cg are the one-column case of the same code.  Per column the arithmetic is the reference's
 // (/root/reference/src/iterativeLinearSolvers.jl:99-215 cgs, :9-97 cg): a column that converges, breaks down or
 // returns early is frozen with its own (error, iter, flag) while the others go on.
 #pragma once
@@ -29,8 +32,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_bdot2(const T* __restrict__ a1, const T* __restrict__ b1, long long ld1, const T* __restrict__ a2, const T* __restrict__ b2,
         long long ld2, long long n, double* __restrict__ partials, unsigned* __restrict__ counters, KState* __restrict__ st,
-        int only_active) {
-    const int j = blockIdx.y;
+        int only_active, const int* __restrict__ colmap) {
+    const int j = colmap ? colmap[blockIdx.y] : blockIdx.y;
     if (only_active && !st[j].active) return;
     const T* pa1 = a1 + j * ld1; const T* pb1 = b1 + j * ld1;
     const T* pa2 = a2 ? a2 + j * ld2 : nullptr; const T* pb2 = b2 ? b2 + j * ld2 : nullptr;
@@ -71,7 +74,7 @@ k_bdot2(const T* __restrict__ a1, const T* __restrict__ b1, long long ld1, const
 // ---- per-column scalar steps (one thread per column) ---------------------------------------------------------
 enum KStep : int { KS_BNRM = 0, KS_INIT_CGS, KS_INIT_CG, KS_RHO0, KS_CGS_BEGIN, KS_CGS_ALPHA, KS_CGS_END, KS_CG_BEGIN, KS_CG_ALPHA, KS_CG_END };
 
-__global__ void k_kstep(KState* __restrict__ st, int ncols, int step, int it, int max_it, double tol, int* __restrict__ nactive) {
+__global__ void k_kstep(KState* __restrict__ st, int ncols, int step, int it, int max_it, double tol) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ncols) return;
     KState& s = st[j];
@@ -87,7 +90,6 @@ __global__ void k_kstep(KState* __restrict__ st, int ncols, int step, int it, in
         s.error = sqrt(s.dot[0]) / s.bnrm2;
         if (s.error < tol) { s.active = 0; s.flag = (step == KS_INIT_CG) ? 2 : 0; }
         else if (max_it <= 0) { s.active = 0; s.flag = (step == KS_INIT_CG) ? 1 : -1; }    // empty loop: :205-213 with rho == 0 / :93-95
-        if (s.active) atomicAdd(nactive, 1);
         break;
     case KS_RHO0:
         s.rhon[0] = s.dot[0]; s.rhon[1] = s.dot[1];
@@ -116,7 +118,6 @@ __global__ void k_kstep(KState* __restrict__ st, int ncols, int step, int it, in
             s.rho1[0] = s.rho[0]; s.rho1[1] = s.rho[1];
             if (it == max_it) { s.active = 0; s.flag = 1; }
         }
-        if (s.active) atomicAdd(nactive, 1);
         break;
     case KS_CG_BEGIN:                               // :67-68
         if (!s.active) break;
@@ -133,23 +134,50 @@ __global__ void k_kstep(KState* __restrict__ st, int ncols, int step, int it, in
             s.rho1[0] = s.rho[0]; s.rho1[1] = s.rho[1];
             if (it == max_it) { s.active = 0; s.flag = 1; }
         }
-        if (s.active) atomicAdd(nactive, 1);
         break;
     }
 }
 
-// ---- vector sweeps over a chunk: grid (x over n, y = column); frozen columns are skipped ---------------------------
+// Stable partition of the column indices: colmap[0 .. nact) = columns still iterating (ascending), colmap[nact .. ncols)
+// = frozen columns (ascending); *nactive = nact.  One CTA; the tail matters because a launch sized with a stale (larger)
+// count must still see every column at most once.
+__global__ void __launch_bounds__(1024) k_compact(const KState* __restrict__ st, int ncols, int* __restrict__ colmap,
+                                                  int* __restrict__ nactive) {
+    __shared__ int wsum[32];
+    __shared__ int base;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int pass = 0; pass < 2; ++pass) {                 // pass 0: active columns, pass 1: the rest
+        if (pass == 0) { if (threadIdx.x == 0) base = 0; __syncthreads(); }
+        for (int j0 = 0; j0 < ncols; j0 += 1024) {
+            const int j = j0 + threadIdx.x;
+            const bool sel = (j < ncols) && ((st[j].active != 0) == (pass == 0));
+            const unsigned m = __ballot_sync(0xffffffffu, sel);
+            if (lane == 0) wsum[w] = __popc(m);
+            __syncthreads();
+            int off = base;
+            for (int i = 0; i < w; ++i) off += wsum[i];
+            if (sel) colmap[off + __popc(m & ((1u << lane) - 1u))] = j;
+            __syncthreads();
+            if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < 32; ++i) t += wsum[i]; base += t; }
+            __syncthreads();
+        }
+        if (pass == 0 && threadIdx.x == 0) *nactive = base;
+        __syncthreads();
+    }
+}
+
+// ---- vector sweeps over a chunk: grid (x over n, y = logical column); frozen columns are skipped ------------------
 #define TB_KCOL_LOOP(nn)                                                                                         \
-    const int j = blockIdx.y;                                                                                    \
     if (!st[j].active) return;                                                                                   \
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (nn); i += (long long)gridDim.x * blockDim.x)
 
 // cgs :168-177
 template <typename T>
 __global__ void k_bcgs_dir(T* __restrict__ u, T* __restrict__ p, const T* __restrict__ r, const T* __restrict__ q,
-                           const KState* __restrict__ st, int first, long long n, long long ld) {
-    const double2 beta = make_double2(st[blockIdx.y].beta[0], st[blockIdx.y].beta[1]);
-    const long long o = blockIdx.y * ld;
+                           const KState* __restrict__ st, int first, long long n, long long ld, const int* __restrict__ colmap) {
+    const int j = colmap ? colmap[blockIdx.y] : blockIdx.y;
+    const double2 beta = make_double2(st[j].beta[0], st[j].beta[1]);
+    const long long o = j * ld;
     TB_KCOL_LOOP(n) {
         if (first) { const T rv = r[o + i]; u[o + i] = rv; p[o + i] = rv; }
         else {
@@ -163,9 +191,10 @@ __global__ void k_bcgs_dir(T* __restrict__ u, T* __restrict__ p, const T* __rest
 // cgs :185-188
 template <typename T>
 __global__ void k_bcgs_q(T* __restrict__ q, T* __restrict__ uh, const T* __restrict__ u, const T* __restrict__ vh,
-                         const KState* __restrict__ st, long long n, long long ld) {
-    const double2 alpha = make_double2(st[blockIdx.y].alpha[0], st[blockIdx.y].alpha[1]);
-    const long long o = blockIdx.y * ld;
+                         const KState* __restrict__ st, long long n, long long ld, const int* __restrict__ colmap) {
+    const int j = colmap ? colmap[blockIdx.y] : blockIdx.y;
+    const double2 alpha = make_double2(st[j].alpha[0], st[j].alpha[1]);
+    const long long o = j * ld;
     TB_KCOL_LOOP(n) {
         const T uv = u[o + i];
         const T qv = v_sub(uv, s_mul<T>(alpha, vh[o + i]));
@@ -173,23 +202,34 @@ __global__ void k_bcgs_q(T* __restrict__ q, T* __restrict__ uh, const T* __restr
         uh[o + i] = v_add(uv, qv);
     }
 }
-// cgs :192-196 and cg :81-84:  x += alpha*d ; r -= alpha*Ad
+// cg :81-84:  x += alpha*d ; r -= alpha*Ad
 template <typename T>
 __global__ void k_bxr(T* __restrict__ x, long long ldx, T* __restrict__ r, const T* __restrict__ d, const T* __restrict__ Ad,
-                      const KState* __restrict__ st, long long n, long long ld) {
-    const double2 alpha = make_double2(st[blockIdx.y].alpha[0], st[blockIdx.y].alpha[1]);
-    const long long o = blockIdx.y * ld, ox = blockIdx.y * ldx;
+                      const KState* __restrict__ st, long long n, long long ld, const int* __restrict__ colmap) {
+    const int j = colmap ? colmap[blockIdx.y] : blockIdx.y;
+    const double2 alpha = make_double2(st[j].alpha[0], st[j].alpha[1]);
+    const long long o = j * ld, ox = j * ldx;
     TB_KCOL_LOOP(n) {
         x[ox + i] = v_add(x[ox + i], s_mul<T>(alpha, d[o + i]));
         r[o + i] = v_sub(r[o + i], s_mul<T>(alpha, Ad[o + i]));
     }
 }
+// cgs :192-194:  x += alpha*d  (the residual update r -= alpha*A*uh, :196, is the epilogue of the product itself)
+template <typename T>
+__global__ void k_bx(T* __restrict__ x, long long ldx, const T* __restrict__ d, const KState* __restrict__ st, long long n,
+                     long long ld, const int* __restrict__ colmap) {
+    const int j = colmap ? colmap[blockIdx.y] : blockIdx.y;
+    const double2 alpha = make_double2(st[j].alpha[0], st[j].alpha[1]);
+    const long long o = j * ld, ox = j * ldx;
+    TB_KCOL_LOOP(n) { x[ox + i] = v_add(x[ox + i], s_mul<T>(alpha, d[o + i])); }
+}
 // cg :69-76
 template <typename T>
 __global__ void k_bcg_dir(T* __restrict__ p, const T* __restrict__ z, const KState* __restrict__ st, int first, long long n,
-                          long long ld) {
-    const double2 beta = make_double2(st[blockIdx.y].beta[0], st[blockIdx.y].beta[1]);
-    const long long o = blockIdx.y * ld;
+                          long long ld, const int* __restrict__ colmap) {
+    const int j = colmap ? colmap[blockIdx.y] : blockIdx.y;
+    const double2 beta = make_double2(st[j].beta[0], st[j].beta[1]);
+    const long long o = j * ld;
     TB_KCOL_LOOP(n) { p[o + i] = first ? z[o + i] : v_add(z[o + i], s_mul<T>(beta, p[o + i])); }
 }
 
