@@ -71,14 +71,16 @@ def bind_to_gpu_numa(local: int):
     memory is first-touched next to the PCIe root complex it will stream through.  Best effort."""
     info = {"numa_node": None, "cores": None}
     try:
-        import torch
-        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
-        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
-        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
-        if bus is None:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = vis.split(",")[local] if vis else str(local)
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", idx],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
             return info
-        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:], rest)
         node = int(open(path).read().strip())
+        info["numa_node"] = node
         if node < 0:
             return info
         cl = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
@@ -89,9 +91,9 @@ def bind_to_gpu_numa(local: int):
         allowed = cpus & set(os.sched_getaffinity(0))
         if allowed:
             os.sched_setaffinity(0, allowed)
-            info = {"numa_node": node, "cores": len(allowed)}
-    except Exception:
-        pass
+            info["cores"] = len(allowed)
+    except Exception as e:
+        info["error"] = str(e)[:80]
     return info
 
 

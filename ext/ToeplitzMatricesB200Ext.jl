@@ -42,6 +42,8 @@ dtcode(::Type{Float32}) = Cint(0); dtcode(::Type{Float64}) = Cint(1)
 dtcode(::Type{ComplexF32}) = Cint(2); dtcode(::Type{ComplexF64}) = Cint(3)
 kindcode(::Toeplitz) = Cint(0); kindcode(::SymmetricToeplitz) = Cint(1); kindcode(::Circulant) = Cint(2)
 kindcode(::LowerTriangularToeplitz) = Cint(3); kindcode(::UpperTriangularToeplitz) = Cint(4); kindcode(::Hankel) = Cint(5)
+kindcode(::Type{<:Toeplitz}) = Cint(0); kindcode(::Type{<:SymmetricToeplitz}) = Cint(1); kindcode(::Type{<:Circulant}) = Cint(2)
+kindcode(::Type{<:LowerTriangularToeplitz}) = Cint(3); kindcode(::Type{<:UpperTriangularToeplitz}) = Cint(4); kindcode(::Type{<:Hankel}) = Cint(5)
 devptr(x) = Ptr{Cvoid}(UInt(pointer(x)))
 curstream() = Ptr{Cvoid}(UInt(stream().handle))
 ab(z::Number) = (c = ComplexF64(z); Cdouble[real(c), imag(c)])
@@ -272,5 +274,40 @@ function _tri_inv_lower(v::DV{T}) where {T}
 end
 inv(A::LowerTriangularToeplitz{T,<:DV}) where {T} = LowerTriangularToeplitz(_tri_inv_lower(A.v))
 inv(A::UpperTriangularToeplitz{T,<:DV}) where {T} = UpperTriangularToeplitz(_tri_inv_lower(A.v))
+
+# ---- multi-GPU: one Julia process driving several devices ------------------------------------------------------
+# Batches shard by columns / systems with no data-path collective (each device multiplies its own column block with
+# its own handle).  The only exchange is the spectrum, once per factorization: factorize on the root device, create
+# empty handles of the same shape on the others, tb200_bcast_spectrum (ncclBroadcast over NVLink, bound inside the
+# library with dlopen -- no NCCL.jl needed).  A handle may be used from several tasks / streams at once: workspaces
+# are keyed by stream (the reference's factorization shares one `tmp`, src/ToeplitzMatrices.jl:97-101).
+mutable struct B200Comm
+    handle::Ptr{Cvoid}
+    ndev::Int
+    function B200Comm(devs::Vector{Cint})
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:tb200_comm_init, libtb), Cint, (Cint, Ptr{Cint}, Ptr{Ptr{Cvoid}}), length(devs), devs, h))
+        c = new(h[], length(devs))
+        finalizer(c -> ccall((:tb200_comm_destroy, libtb), Cint, (Ptr{Cvoid},), c.handle), c)
+        return c
+    end
+end
+
+"Empty factorization of the same shape on the CURRENT device (filled by `bcast_spectrum!`)."
+function similar_factorization(F::B200ToeplitzFactorization{T,A}) where {T,A}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    m, n = size(F)
+    check(ccall((:tb200_factorize_empty, libtb), Cint, (Cint, Cint, Int64, Int64, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
+                kindcode(A), dtcode(T), m, n, curstream(), h))
+    return B200ToeplitzFactorization{T,A}(h[], (m, n))
+end
+
+"`Fs[i]` lives on device `i` of the communicator; `root` (0-based) owns the spectrum."
+function bcast_spectrum!(comm::B200Comm, Fs::Vector{<:B200ToeplitzFactorization}, root::Integer, streams::Vector{Ptr{Cvoid}})
+    hs = Ptr{Cvoid}[F.handle for F in Fs]
+    check(ccall((:tb200_bcast_spectrum, libtb), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint, Cint, Ptr{Ptr{Cvoid}}),
+                comm.handle, hs, length(hs), root, streams))
+    return Fs
+end
 
 end # module

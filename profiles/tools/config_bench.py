@@ -151,14 +151,16 @@ def sweep():
         del X, Y, F
 
 
-def c6():
+def c6(seeds=(0,)):
     """Toeplitz \\ B with many right-hand sides: batched cgs + Strang vs the reference's column loop of single solves."""
-    for n, l in ((1 << 16, 256), (1 << 20, 64)):
+    for n, l, seed in [(1 << 16, 256, sd) for sd in seeds] + [(1 << 20, 64, 0)]:
         k = np.arange(n, dtype=np.float64)
         A = tb.Toeplitz(torch.from_numpy(0.9 ** k).cuda(), torch.from_numpy(0.4 ** k).cuda())
         FA, M = tb.factorize(A), tb.factorize(tb.strang(A))
         B = tb.colmajor(n, l)
-        B.copy_(torch.randn(n, l, dtype=torch.float64, device="cuda"))
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(seed)
+        B.copy_(torch.randn(n, l, dtype=torch.float64, device="cuda", generator=gen))
         tol = 100 * 2.220446049250313e-16
         X = tb.colmajor(n, l)
 
@@ -176,9 +178,15 @@ def c6():
         looped(2)
         torch.cuda.synchronize()
         t0 = time.perf_counter(); looped(8); torch.cuda.synchronize(); tl = (time.perf_counter() - t0) / 8
-        out(config="C6 Toeplitz{Float64} n=2^%d \\ %d right-hand sides, cgs + Strang" % (int(np.log2(n)), l),
+        out(config="C6 Toeplitz{Float64} n=2^%d \\ %d right-hand sides, cgs + Strang, seed %d" % (int(np.log2(n)), l, seed),
+            iteration_histogram={int(k): int(v) for k, v in zip(*np.unique(np.minimum(its, 1000), return_counts=True))},
             batched_solves_per_s=l / tb_, column_loop_solves_per_s=1.0 / tl, iterations=[min(its), max(its)],
             flags=sorted(set(flags)), max_rel_residual=max(errs))
+
+
+def c6scan():
+    """look for right-hand-side draws with a straggler column (one column running to max_it while the rest stop at 3-6)"""
+    c6(seeds=tuple(range(12)))
 
 
 if __name__ == "__main__":

@@ -153,3 +153,33 @@ def test_largest_float64_embedding(tb):
         z = torch.zeros(1 << 25, dtype=torch.float64, device="cuda")
         z[0] = 1
         tb.factorize(tb.SymmetricToeplitz(z))          # embedding 2^26 exceeds the Float64 plan: refused, no fallback
+
+
+@pytest.mark.parametrize("n", [257, 300, 384, 385, 500, 512])
+def test_levinson_durbin_shared_memory_x_variant(tb, n):
+    """Register-lean kernels of csrc/levinson_sx.cu (option lev_sx): same systems as the register kernels, 1e-12."""
+    def dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+    def devmat(a):
+        return torch.from_numpy(np.ascontiguousarray(a.T)).cuda().t()
+
+    rng = np.random.default_rng(n)
+    ns = 37
+    R = np.asfortranarray(rng.random((n - 1, ns)) / n)
+    B = np.asfortranarray(rng.standard_normal((n, ns)))
+    Rd = np.asfortranarray(rng.random((n, ns)) / n)
+    diag = 1.0 + rng.random(ns)
+    try:
+        tb.set_option("lev_sx", 3)
+        X = tb.colmajor(n, ns)
+        tb.levinson_(X, devmat(R), devmat(B))
+        Y = tb.colmajor(n, ns)
+        tb.durbin_(Y, devmat(Rd))
+        Xd = tb.colmajor(n, ns)
+        tb.levinson_(Xd, devmat(R * diag), devmat(B), dev(diag))
+    finally:
+        tb.set_option("lev_sx", 0)
+    assert rel(X.cpu().numpy(), OC.c_levinson_batched(R, B)) <= 1e-12
+    assert rel(Y.cpu().numpy(), OC.c_durbin_batched(Rd)) <= 1e-12
+    assert rel(Xd.cpu().numpy(), OC.c_levinson_batched(R, B) / diag) <= 1e-12

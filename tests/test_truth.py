@@ -134,7 +134,7 @@ def device_matrices(tb, n, dtype):
         "toeplitz": tb.Toeplitz(dev(vc), dev(vr)), "toeplitz_adj": tb.adjoint(tb.Toeplitz(dev(vc), dev(vr))),
         "symmetric": tb.SymmetricToeplitz(dev(vc)), "circulant": tb.Circulant(dev(vc)),
         "lower": tb.LowerTriangularToeplitz(dev(vc)), "upper": tb.UpperTriangularToeplitz(dev(vc)),
-        "hankel": tb.Hankel(dev((0.9 ** k[::-1]).astype(dtype)), dev(vr)),
+        "hankel": tb.Hankel(dev((0.9 ** k[::-1]).astype(dtype)), vr=dev(vr)),
     }
 
 

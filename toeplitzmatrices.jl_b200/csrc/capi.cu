@@ -32,8 +32,9 @@ static std::atomic<long long> g_group_bytes{48ll << 20};   // two-level scratch 
 static std::atomic<long long> g_host_chunk_bytes{256ll << 20};
 static std::atomic<long long> g_krylov_work_bytes{16ll << 30};   // work-vector budget of the batched cgs / cg (columns per chunk)
 static std::atomic<int> g_time_passes{0};
-static std::atomic<int> g_l2_persist_mb{0};      // persisting-L2 carve-out for the two-level workspaces (0 = off)
+static std::atomic<int> g_l2_persist_mb{64};     // persisting-L2 carve-out for the two-level workspaces (0 = off); +4 % on config 2
 static std::atomic<int> g_tma{0};                // TMA-staged strided passes (tma_cols.cuh) where eligible; measured, see DESIGN.md
+extern int g_lev_sx;                             // levinson.cu
 int g_prune_half = 1;                            // pruned pass A / pass C when half of the embedding is padding
 static std::atomic<int> g_overlap_streams{2};   // helper streams for group overlap (0/1 = off)
 static std::atomic<int> g_l2max_f64{12}, g_l2max_f32{13}, g_ta_cap{0}, g_force_l1{0};
@@ -850,6 +851,7 @@ int tb200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "host_chunk_bytes")) { g_host_chunk_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "time_passes")) { g_time_passes = value ? 1 : 0; return TB200_OK; }
     if (!strcmp(name, "l2_persist_mb")) { g_l2_persist_mb = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 1024); return TB200_OK; }
+    if (!strcmp(name, "lev_sx")) { g_lev_sx = (int)(value & 3); return TB200_OK; }
     if (!strcmp(name, "prune_half")) { g_prune_half = value ? 1 : 0; return TB200_OK; }
     if (!strcmp(name, "tma")) { g_tma = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 3); return TB200_OK; }   // bit 0: pass A loads, bit 1: pass C stores
     if (!strcmp(name, "overlap_streams")) { g_overlap_streams = (int)std::min<int64_t>(std::max<int64_t>(value, 0), tb200_fact::MAXS); return TB200_OK; }

@@ -4,6 +4,8 @@
 
 namespace tb {
 
+int g_lev_sx = 0;
+
 
 // Fallback for n > 512: one CTA per system, iterates in shared memory (double-buffered y).
 template <typename R, bool DURBIN>
@@ -82,6 +84,11 @@ static int launch_levinson(int64_t n, int64_t nsys, const R* r, int64_t ldr, con
         const cudaError_t e = launch_levinson_small<R, DURBIN>(n, nsys, r, ldr, b, ldb, x, ldx, diag, s);
         count_launch();
         return cuda_status(e, "levinson warp kernel (several systems per warp)");
+    }
+    if (n > 2 * LSPAN && n <= 4 * LSPAN && (g_lev_sx & (DURBIN ? 2 : 1))) {
+        const cudaError_t e = launch_levinson_sx<R, DURBIN>(n, nsys, r, ldr, b, ldb, x, ldx, diag, s);
+        count_launch();
+        return cuda_status(e, "levinson warp kernel (shared-memory x)");
     }
     if (n <= 4 * LSPAN) {
         const int S = (int)((n + LSPAN - 1) / LSPAN);

@@ -220,4 +220,10 @@ template <typename R, bool DURBIN>
 cudaError_t launch_levinson_mw(int64_t n, int64_t nsys, const R* r, int64_t ldr, const R* b, int64_t ldb, R* x, int64_t ldx,
                                const R* diag, cudaStream_t s);
 
+// register-lean variant for 256 < n <= 512 (levinson_sx.cu): x and reverse(r) in shared memory
+template <typename R, bool DURBIN>
+cudaError_t launch_levinson_sx(int64_t n, int64_t nsys, const R* r, int64_t ldr, const R* b, int64_t ldb, R* x, int64_t ldx,
+                               const R* diag, cudaStream_t s);
+extern int g_lev_sx;      // bit 0: Levinson, bit 1: Durbin take the sx kernels (tb200_set_option("lev_sx"))
+
 }  // namespace tb
