@@ -51,21 +51,21 @@ out = tb.mul(F, Xd)
 tb.set_option("tma", 0)
 assert torch.equal(out, ref)
 
-# Levinson / Durbin: lane groups, one warp, shared-memory-x variant, multi-warp, block fallback
+# Levinson / Durbin: lane groups, one warp, generator form, multi-warp, block fallback
 for n in ((40, 130, 300, 500, 600, 2100) if not LIGHT else (40, 130, 300, 500, 600)):
     ns = 9
     R = np.asfortranarray(rng.random((n - 1, ns)) / n)
     B = np.asfortranarray(rng.standard_normal((n, ns)))
-    for sx in (0, 3):
-        tb.set_option("lev_sx", sx)
+    for sx in (1, 0):
+        tb.set_option("lev_gen", sx)
         Xl = tb.colmajor(n, ns)
         tb.levinson_(Xl, devmat(R), devmat(B))
-        chk("levinson n=%d sx=%d" % (n, sx), rel(Xl.cpu().numpy(), OC.c_levinson_batched(R, B)), 1e-12)
+        chk("levinson n=%d gen=%d" % (n, sx), rel(Xl.cpu().numpy(), OC.c_levinson_batched(R, B)), 1e-12)
         Rd = np.asfortranarray(rng.random((n, ns)) / n)
         Yl = tb.colmajor(n, ns)
         tb.durbin_(Yl, devmat(Rd))
-        chk("durbin n=%d sx=%d" % (n, sx), rel(Yl.cpu().numpy(), OC.c_durbin_batched(Rd)), 1e-12)
-    tb.set_option("lev_sx", 0)
+        chk("durbin n=%d gen=%d" % (n, sx), rel(Yl.cpu().numpy(), OC.c_durbin_batched(Rd)), 1e-12)
+    tb.set_option("lev_gen", 1)
 a = np.concatenate([[1.0], rng.random(299) / 300])
 Bm = rng.standard_normal((300, 6))
 chk("levinson multirhs", rel(tb.levinson(tb.SymmetricToeplitz(dev(a)), devmat(Bm)).cpu().numpy(), np.linalg.solve(O.SymmetricToeplitz(a).dense(), Bm)), 1e-10)

@@ -155,31 +155,39 @@ def test_largest_float64_embedding(tb):
         tb.factorize(tb.SymmetricToeplitz(z))          # embedding 2^26 exceeds the Float64 plan: refused, no fallback
 
 
-@pytest.mark.parametrize("n", [257, 300, 384, 385, 500, 512])
-def test_levinson_durbin_shared_memory_x_variant(tb, n):
-    """Register-lean kernels of csrc/levinson_sx.cu (option lev_sx): same systems as the register kernels, 1e-12."""
+@pytest.mark.parametrize("n", [2, 3, 5, 16, 17, 33, 64, 65, 100, 128, 129, 200, 256, 257, 300, 384, 385, 500, 511, 512])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_levinson_durbin_both_kernel_families(tb, n, dtype):
+    """Generator-form kernels (csrc/levinson_gen.cu, the default for n <= 512) and the dot-product kernels (option
+    lev_gen=0) against the C oracle of src/directLinearSolvers.jl:15-28,100-134 on the same systems, incl. the diag
+    normalisation of levinson(T, b), at the north_star tolerances."""
     def dev(a):
         return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
     def devmat(a):
         return torch.from_numpy(np.ascontiguousarray(a.T)).cuda().t()
 
+    dt = np.dtype(dtype)
+    tol = 1e-12 if dt == np.float64 else 1e-5
     rng = np.random.default_rng(n)
     ns = 37
-    R = np.asfortranarray(rng.random((n - 1, ns)) / n)
-    B = np.asfortranarray(rng.standard_normal((n, ns)))
-    Rd = np.asfortranarray(rng.random((n, ns)) / n)
-    diag = 1.0 + rng.random(ns)
-    try:
-        tb.set_option("lev_sx", 3)
-        X = tb.colmajor(n, ns)
-        tb.levinson_(X, devmat(R), devmat(B))
-        Y = tb.colmajor(n, ns)
-        tb.durbin_(Y, devmat(Rd))
-        Xd = tb.colmajor(n, ns)
-        tb.levinson_(Xd, devmat(R * diag), devmat(B), dev(diag))
-    finally:
-        tb.set_option("lev_sx", 0)
-    assert rel(X.cpu().numpy(), OC.c_levinson_batched(R, B)) <= 1e-12
-    assert rel(Y.cpu().numpy(), OC.c_durbin_batched(Rd)) <= 1e-12
-    assert rel(Xd.cpu().numpy(), OC.c_levinson_batched(R, B) / diag) <= 1e-12
+    R = np.asfortranarray(rng.random((max(n - 1, 0), ns)) / n).astype(dt)
+    B = np.asfortranarray(rng.standard_normal((n, ns))).astype(dt)
+    Rd = np.asfortranarray(rng.random((n, ns)) / n).astype(dt)
+    diag = (1.0 + rng.random(ns)).astype(dt)
+    xo = OC.c_levinson_batched(np.asfortranarray(R.astype(np.float64)), np.asfortranarray(B.astype(np.float64)))
+    yo = OC.c_durbin_batched(np.asfortranarray(Rd.astype(np.float64)))
+    for gen in (1, 0):
+        try:
+            tb.set_option("lev_gen", gen)
+            X = tb.colmajor(n, ns, getattr(torch, dtype))
+            tb.levinson_(X, devmat(R), devmat(B))
+            Y = tb.colmajor(n, ns, getattr(torch, dtype))
+            tb.durbin_(Y, devmat(Rd))
+            Xd = tb.colmajor(n, ns, getattr(torch, dtype))
+            tb.levinson_(Xd, devmat(R * diag), devmat(B), dev(diag))
+        finally:
+            tb.set_option("lev_gen", 1)
+        assert rel(X.cpu().numpy(), xo) <= tol, ("levinson", gen)
+        assert rel(Y.cpu().numpy(), yo) <= tol, ("durbin", gen)
+        assert rel(Xd.cpu().numpy(), xo / diag.astype(np.float64)) <= tol, ("levinson diag", gen)

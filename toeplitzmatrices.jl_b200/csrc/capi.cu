@@ -34,7 +34,7 @@ static std::atomic<long long> g_krylov_work_bytes{16ll << 30};   // work-vector 
 static std::atomic<int> g_time_passes{0};
 static std::atomic<int> g_l2_persist_mb{64};     // persisting-L2 carve-out for the two-level workspaces (0 = off); +4 % on config 2
 static std::atomic<int> g_tma{0};                // TMA-staged strided passes (tma_cols.cuh) where eligible; measured, see DESIGN.md
-extern int g_lev_sx;                             // levinson.cu
+extern int g_lev_gen;                            // levinson.cu
 int g_prune_half = 1;                            // pruned pass A / pass C when half of the embedding is padding
 static std::atomic<int> g_overlap_streams{2};   // helper streams for group overlap (0/1 = off)
 static std::atomic<int> g_l2max_f64{12}, g_l2max_f32{13}, g_ta_cap{0}, g_force_l1{0};
@@ -257,6 +257,7 @@ struct StreamWork {
     std::shared_ptr<DevBuf> scratch, scratch_extra[MAXS], bs_u, bs_v;
     cudaStream_t hs[MAXS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[MAXS] = {nullptr, nullptr, nullptr, nullptr};
+    bool win_set[MAXS] = {false, false, false, false};     // a persisting-L2 window is currently set on hs[i] (or the user stream)
     ~StreamWork() {
         for (int i = 0; i < MAXS; ++i) {
             if (hs[i]) cudaStreamDestroy(hs[i]);
@@ -549,8 +550,18 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
         for (int i = 0; i < nstr; ++i) TB_CUDA(cudaStreamWaitEvent(w->hs[i], w->ev_fork, 0), "fork");
     }
     cudaStream_t user_stream = s;
-    const bool l2win = g_l2_persist_mb.load() > 0;
-    if (l2win) for (int i = 0; i < nstr; ++i) apply_l2_window(stream_of[i], scratch_of[i], (size_t)G * Np * sizeof(cx<R>), nstr);
+    // the window pays only when the workspaces in flight fit the carve-out as a whole (config 2: 2 x 32 MiB); larger
+    // ones (2 x 64 MiB of config 3, 256 MiB of config 5) stream through DRAM anyway and a partial window costs them
+    // 15-30 % (profiles/experiments_r02.md)
+    const size_t ws_in_flight = (size_t)nstr * (size_t)G * Np * sizeof(cx<R>);
+    const bool l2win = g_l2_persist_mb.load() > 0 && ws_in_flight <= ((size_t)g_l2_persist_mb.load() << 20);
+    static std::atomic<bool> persisting_lines{false};        // lines tagged persisting may still sit in the carve-out
+    if (l2win) persisting_lines = true;
+    else if (persisting_lines.exchange(false)) cudaCtxResetPersistingL2Cache();   // give the carve-out back to normal traffic
+    for (int i = 0; i < nstr; ++i) {
+        if (l2win) { apply_l2_window(stream_of[i], scratch_of[i], (size_t)G * Np * sizeof(cx<R>), nstr); w->win_set[i] = true; }
+        else if (w->win_set[i]) { apply_l2_window(stream_of[i], nullptr, 0, 1); w->win_set[i] = false; }
+    }
     a.log2n2 = h->log2l2;
     a.tw_lo = reinterpret_cast<const cx<R>*>(h->tw_lo->p);
     a.tw_hi = reinterpret_cast<const cx<R>*>(h->tw_hi->p);
@@ -652,7 +663,7 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
             TB_CUDA(launch_colsC<R>(h->log2l1, h->ta, pc, s), "k_colsC");
         }
     }
-    if (l2win && !overlap) apply_l2_window(user_stream, nullptr, 0, 1);      // never leave a window on the caller's stream
+    if (l2win && !overlap) { apply_l2_window(user_stream, nullptr, 0, 1); w->win_set[0] = false; }   // never leave a window on the caller's stream
     if (overlap) {
         for (int i = 0; i < nstr; ++i) {
             TB_CUDA(cudaEventRecord(w->ev_join[i], w->hs[i]), "join");
@@ -851,7 +862,7 @@ int tb200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "host_chunk_bytes")) { g_host_chunk_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "time_passes")) { g_time_passes = value ? 1 : 0; return TB200_OK; }
     if (!strcmp(name, "l2_persist_mb")) { g_l2_persist_mb = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 1024); return TB200_OK; }
-    if (!strcmp(name, "lev_sx")) { g_lev_sx = (int)(value & 3); return TB200_OK; }
+    if (!strcmp(name, "lev_gen")) { g_lev_gen = (int)(value & 1); return TB200_OK; }
     if (!strcmp(name, "prune_half")) { g_prune_half = value ? 1 : 0; return TB200_OK; }
     if (!strcmp(name, "tma")) { g_tma = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 3); return TB200_OK; }   // bit 0: pass A loads, bit 1: pass C stores
     if (!strcmp(name, "overlap_streams")) { g_overlap_streams = (int)std::min<int64_t>(std::max<int64_t>(value, 0), tb200_fact::MAXS); return TB200_OK; }

@@ -4,7 +4,7 @@
 
 namespace tb {
 
-int g_lev_sx = 0;
+int g_lev_gen = 1;
 
 
 // Fallback for n > 512: one CTA per system, iterates in shared memory (double-buffered y).
@@ -80,15 +80,15 @@ template <typename R, bool DURBIN>
 static int launch_levinson(int64_t n, int64_t nsys, const R* r, int64_t ldr, const R* b, int64_t ldb, R* x,
                            int64_t ldx, const R* diag, cudaStream_t s) {
     if (nsys <= 0 || n <= 0) return TB200_OK;
+    if (n <= 4 * LSPAN && g_lev_gen) {         // generator form: no reductions (levinson_gen.cu)
+        const cudaError_t e = launch_levinson_gen<R, DURBIN>(n, nsys, r, ldr, b, ldb, x, ldx, diag, s);
+        count_launch();
+        return cuda_status(e, "levinson generator-form kernel");
+    }
     if (n <= 4 * 16 * LB) {                   // small orders: 8 (n <= 64), 4 (n <= 128) or 2 (n <= 256) systems per warp
         const cudaError_t e = launch_levinson_small<R, DURBIN>(n, nsys, r, ldr, b, ldb, x, ldx, diag, s);
         count_launch();
         return cuda_status(e, "levinson warp kernel (several systems per warp)");
-    }
-    if (n > 2 * LSPAN && n <= 4 * LSPAN && (g_lev_sx & (DURBIN ? 2 : 1))) {
-        const cudaError_t e = launch_levinson_sx<R, DURBIN>(n, nsys, r, ldr, b, ldb, x, ldx, diag, s);
-        count_launch();
-        return cuda_status(e, "levinson warp kernel (shared-memory x)");
     }
     if (n <= 4 * LSPAN) {
         const int S = (int)((n + LSPAN - 1) / LSPAN);

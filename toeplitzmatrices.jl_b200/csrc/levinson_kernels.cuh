@@ -56,6 +56,17 @@ __device__ __forceinline__ double fast_rcp(double x) {
     e = fma(-x, y, 1.0);
     return fma(y, e, y);
 }
+// same with two Newton steps: the seed carries >= 20 bits, so two steps reach the rounding floor (<= 2 ulp); the third
+// step of fast_rcp only polishes the last bit and sits on the critical alpha -> beta -> 1/beta -> alpha chain
+__device__ __forceinline__ double fast_rcp2(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ float fast_rcp2(float x) { return 1.0f / x; }
 __device__ __forceinline__ float fast_rcp(float x) { return 1.0f / x; }
 
 // Shifting vectors (yh, rh) are never moved between registers: a compile-time phase ph (= number of shifts so far
@@ -220,10 +231,10 @@ template <typename R, bool DURBIN>
 cudaError_t launch_levinson_mw(int64_t n, int64_t nsys, const R* r, int64_t ldr, const R* b, int64_t ldb, R* x, int64_t ldx,
                                const R* diag, cudaStream_t s);
 
-// register-lean variant for 256 < n <= 512 (levinson_sx.cu): x and reverse(r) in shared memory
+// generator (Schur) form for n <= 512: no reductions, 3 FMAs per slot and step (levinson_gen.cu)
 template <typename R, bool DURBIN>
-cudaError_t launch_levinson_sx(int64_t n, int64_t nsys, const R* r, int64_t ldr, const R* b, int64_t ldb, R* x, int64_t ldx,
-                               const R* diag, cudaStream_t s);
-extern int g_lev_sx;      // bit 0: Levinson, bit 1: Durbin take the sx kernels (tb200_set_option("lev_sx"))
+cudaError_t launch_levinson_gen(int64_t n, int64_t nsys, const R* r, int64_t ldr, const R* b, int64_t ldb, R* x, int64_t ldx,
+                                const R* diag, cudaStream_t s);
+extern int g_lev_gen;     // 1 (default): n <= 512 takes the generator-form kernels; 0: the dot-product kernels (tb200_set_option("lev_gen"))
 
 }  // namespace tb
