@@ -399,11 +399,18 @@ def run_configs(tb, rank, world, dist, peak, quick=False):
             lo, hi = max(0, i - 63), min(n, i + 64)
             res_rows.append(b_h[i] - np.dot(col[np.abs(np.arange(lo, hi) - i)], xs_h[lo:hi]))
         res_s = float(np.max(np.abs(res_rows)) / (np.linalg.norm(b_h) / math.sqrt(n)))
+        # the norm the solver reports, recomputed from scratch on the device: ||b - A x|| / ||b||
+        r_dev = bvec - tb.mul(FA, xs)
+        res_true = float(torch.linalg.vector_norm(r_dev) / torch.linalg.vector_norm(bvec))
         gbs = 19 * n * 8 * it / dt / 1e9
         out["C5b"] = {"workload": "SymmetricToeplitz{ComplexF32} n=2^%d, cgs + Strang preconditioner, %d timed iterations (BASELINE configs[4])" % (int(math.log2(n)), it),
                       "iterations_per_s": it / dt, "ms_per_iteration": dt / it * 1e3,
                       "converged": {"iterations": it_c, "flag": flag_c, "rel_residual_reported": err_c, "tol": 1e-5,
-                                    "sampled_true_residual_rel_rms": res_s},
+                                    "true_rel_residual_recomputed": res_true,
+                                    "max_abs_residual_on_sampled_rows_over_rms_b": res_s,
+                                    "note": "rows 0, 5, n/2, n-6, n-1 of the dense definition in complex128; after two Strang-preconditioned "
+                                            "iterations the residual sits in the few boundary rows, so its largest entries are O(1e-2) "
+                                            "while its 2-norm over 2^24 rows is below tol"},
                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                                    "alg_bytes_per_unit": 19 * n * 8, "note": "19 n-vector sweeps per iteration (SURVEY 8d) + 8 FFT applications"}}
         del FA, Mp, A, bvec, xs
@@ -534,7 +541,7 @@ def run_ours(args):
     # ---- second timed region of K steps for the roofline leg: every pass bracketed by CUDA events on its
     # launching stream, group overlap off so a pass duration is one kernel's duration (the events and the lost
     # overlap cost ~40 %, which is why `value` comes from the first region)
-    pass_ms = {"cols_A": 0.0, "rows_B": 0.0, "cols_C": 0.0, "rows_single": 0.0}
+    pass_ms = {"cols_A": 0.0, "rows_B": 0.0, "cols_C": 0.0, "rows_single": 0.0, "cols_CA": 0.0}
     pass_cnt = {k: 0 for k in pass_ms}
     if not args.no_pass_events:
         tb.set_option("time_passes", 1)

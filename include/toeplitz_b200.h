@@ -209,6 +209,9 @@ int tb200_set_option(const char* name, int64_t value);
  * this drains them: summed milliseconds and launch counts for {cols A, rows B, cols C,
  * single-kernel rows}.  Synchronises on the recorded events.                            */
 int tb200_pass_times(double ms[4], int64_t counts[4]);
+/* same with n <= 5 entries: entry 4 = the fused "pass C of one group + pass A of the next" launches
+ * (option "ca_fuse"); tb200_pass_times reports those together with cols C.             */
+int tb200_pass_times_ex(double* ms, int64_t* counts, int n);
 
 #ifdef __cplusplus
 }

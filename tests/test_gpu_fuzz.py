@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from oracle import toeplitz_oracle as O
+import parity_tools as PT
 
 pytestmark = pytest.mark.gpu
 
@@ -102,7 +103,9 @@ def test_mul_random_shapes(tb, seed):
         F = tb.factorize(Ad)
         tb.mul_(Yd, F, _devmat_padded(X, 0), alpha, beta)
         ref = alpha * want + beta * Y0
-        assert _rel(Yd.cpu().numpy(), ref) <= 4 * tol, tag + " (alpha, beta)"
+        # alpha*A*x + beta*y can cancel: the error is relative to the two terms, not to their sum
+        cancel = (abs(alpha) * np.linalg.norm(want) + abs(beta) * np.linalg.norm(Y0)) / max(np.linalg.norm(ref), 1e-300)
+        assert _rel(Yd.cpu().numpy(), ref) <= tol * max(1.0, cancel), tag + " (alpha, beta; cancellation %.2f)" % cancel
         # the padding rows of y were not touched
         base = Yd._base if Yd._base is not None else Yd
         assert bool(torch.isnan(torch.view_as_real(base) if base.is_complex() else base).any()) == (Yd.stride(1) > m), tag
@@ -115,11 +118,9 @@ def test_circulant_solves_random_sizes(tb, seed):
     rng = np.random.default_rng(2000 + seed)
     for case in range(10):
         dtype = [np.float64, np.complex128, np.complex64][int(rng.integers(3))]
-        single = np.dtype(dtype) == np.dtype(np.complex64)
         n = max(1, _size(rng, 40000))
         if case % 3 == 0:
             n = 1 << int(rng.integers(0, 16))
-        tol = 2e-4 if single else 1e-10        # ldiv divides by the spectrum: conditioning enters, see below
         v = _rand(rng, n, dtype)
         v[0] += 4.0 * np.sqrt(n)               # keep the spectrum away from zero (|eig| >= ~sqrt(n))
         Co, Cd = O.Circulant(v), tb.Circulant(_dev(v))
@@ -129,10 +130,12 @@ def test_circulant_solves_random_sizes(tb, seed):
         O.ldiv_mat(Co, Bo, O.circ_ldiv)
         Bd = _devmat_padded(B, int(rng.integers(0, 5)))
         tb.ldiv_(Cd, Bd)
-        tag = "seed %d case %d: %s n=%d cols=%d" % (seed, case, np.dtype(dtype).name, n, ncols)
-        assert _rel(Bd.cpu().numpy(), Bo) <= tol, tag
-        assert _rel(tb.eigvals(Cd).cpu().numpy(), np.fft.fft(v.astype(np.complex128))) <= tol, tag + " (eigvals)"
-        assert _rel(tb.inv(Cd).vc.cpu().numpy(), O.circ_inv(Co).vc) <= tol, tag + " (inv)"
+        tag = "fuzz circulant seed %d case %d: %s n=%d cols=%d" % (seed, case, np.dtype(dtype).name, n, ncols)
+        lam = np.fft.fft(v.astype(np.complex128))
+        kC = PT.cond_spectrum(lam)             # ldiv / inv divide by the spectrum: forward error ~ cond * eps on both sides
+        PT.check(tag + " ldiv", Bd.cpu().numpy(), Bo, dtype, kC)
+        PT.check(tag + " eigvals", tb.eigvals(Cd).cpu().numpy(), lam, dtype)
+        PT.check(tag + " inv", tb.inv(Cd).vc.cpu().numpy(), O.circ_inv(Co).vc, dtype, kC)
 
 
 @pytest.mark.parametrize("seed", range(4))

@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from oracle import toeplitz_oracle as O
+import parity_tools as PT
 
 pytestmark = pytest.mark.gpu
 
@@ -45,6 +46,8 @@ def test_cgs_batched_matches_per_column_oracle(tb, dtype):
     B[:, 4] = Ao.dense()[:, 0]                   # solved almost at once: converges well before the others
     tol = 1e-5 if single else 100 * np.finfo(np.float64).eps
     Mo, Md = O.factorize(O.strang(Ao)), tb.factorize(tb.strang(Ad))
+    Dn = Ao.dense().astype(np.complex128)
+    kA = PT.cond2(Dn)                            # KMS(0.5): ~9
     X = tb.colmajor(n, l, _dev(B[:1]).dtype)
     X.zero_()
     X, errs, its, flags = tb.cgs_batched(Ad, X, _devmat(B), Md, 50, tol)
@@ -53,7 +56,8 @@ def test_cgs_batched_matches_per_column_oracle(tb, dtype):
     for j in range(l):
         xo, eo, ito, fo = O.cgs(Ao, np.zeros(n, dtype), B[:, j].copy(), Mo, 50, tol)
         assert flags[j] == fo and abs(its[j] - ito) <= 1, (j, its[j], ito, flags[j], fo)
-        assert _rel(Xh[:, j], xo) <= (1e-4 if single else 1e-10), j
+        # both sides stop at a relative residual <= tol: the solutions agree to cond * (res_o + res_d)
+        PT.check("cgs batched col %d" % j, Xh[:, j], xo, dtype, kA, extra=2.0 * kA * (eo + errs[j]))
         assert errs[j] <= max(10 * eo, tol)
         seen.add(its[j])
     assert its[2] == 0 and len(seen) >= 3        # columns really stopped at different iterations
@@ -65,7 +69,11 @@ def test_cgs_batched_matches_per_column_oracle(tb, dtype):
     for j in range(l):
         xo, eo, ito, fo = O.cgs(Ao, np.zeros(n, dtype), Bn[:, j].copy(), Mo, 3, 0.0)
         assert (its2[j], flags2[j]) == (ito, fo) == (3, 1)
-        assert _rel(X2[:, j].cpu().numpy(), xo) <= (1e-3 if single else 1e-9)
+        # the budget outlasts convergence: iterates agree to cond * (true residual floor), measured on both sides
+        xd = X2[:, j].cpu().numpy()
+        nb = np.linalg.norm(Bn[:, j])
+        floor = (np.linalg.norm(Bn[:, j] - Dn @ xo) + np.linalg.norm(Bn[:, j] - Dn @ xd)) / nb
+        PT.check("cgs batched 3 iterations col %d" % j, xd, xo, dtype, kA, extra=2.0 * kA * floor)
 
 
 def test_cg_batched_matches_per_column_oracle(tb):
@@ -77,6 +85,7 @@ def test_cg_batched_matches_per_column_oracle(tb):
     B[:, 1] = 0                                  # the reference's value-less early return -> flag 2
     tol = 100 * np.finfo(np.float64).eps
     Mo, Md = O.factorize(O.strang(Ao)), tb.factorize(tb.strang(Ad))
+    kA = PT.cond2(Ao.dense())
     X = tb.colmajor(n, l)
     X.zero_()
     X, errs, its, flags = tb.cg_batched(Ad, X, _devmat(B), Md, 60, tol)
@@ -87,7 +96,7 @@ def test_cg_batched_matches_per_column_oracle(tb):
             continue
         xo, eo, ito, fo = res
         assert flags[j] == fo and abs(its[j] - ito) <= 1
-        assert _rel(X[:, j].cpu().numpy(), xo) <= 1e-10
+        PT.check("cg batched col %d" % j, X[:, j].cpu().numpy(), xo, np.float64, kA, extra=2.0 * kA * (eo + errs[j]))
     with pytest.raises(tb.ArgumentError):
         tb.cg_batched(Ad, X.to(torch.complex128), _devmat(B.astype(np.complex128)), Md, 5, tol)
 
@@ -156,6 +165,10 @@ def test_batched_two_level_transforms_with_stragglers(tb, n, l):
     B[:, 3] = Ao.dense()[:, 0] if n <= 8000 else O.matvec(Ao, np.eye(1, n, 0).ravel())
     tol = 100 * np.finfo(np.float64).eps
     Mo, Md = O.factorize(O.strang(Ao)), tb.factorize(tb.strang(Ad))
+    # Toeplitz(0.9^k, 0.4^k): symbol f(z) = 1/(1-0.9z) + 0.4/(z-0.4); cond <= max|f| / min|f| on |z| = 1 (computed on a grid)
+    z = np.exp(2j * np.pi * np.arange(4096) / 4096)
+    f = 1.0 / (1.0 - 0.9 * z) + 0.4 / (z - 0.4)
+    kA = float(np.abs(f).max() / np.abs(f).min())
     tb.set_option("group_bytes", 1 << 20)                     # one pair per group -> several groups per product
     try:
         X = tb.colmajor(n, l)
@@ -168,8 +181,9 @@ def test_batched_two_level_transforms_with_stragglers(tb, n, l):
         xo, eo, ito, fo = O.cgs(Ao, np.zeros(n), B[:, j].copy(), Mo, 12, tol)
         assert abs(its[j] - ito) <= 1, (j, its[j], ito)
         if flags[j] == fo == 0:
-            assert _rel(Xh[:, j], xo) <= 1e-10, j
-        assert np.isfinite(errs[j]) and errs[j] <= max(1e3 * eo, 1e-9), (j, errs[j], eo)
+            PT.check("cgs batched two-level n=%d col %d" % (n, j), Xh[:, j], xo, np.float64, kA, extra=2.0 * kA * (eo + errs[j]))
+        # a column that has not converged inside the budget still reports a finite residual of the oracle's order
+        assert np.isfinite(errs[j]) and errs[j] <= max(1e3 * eo, 1e3 * tol), (j, errs[j], eo)
     # single-vector solver == one-column batched solver
     x1, e1, i1, f1 = tb.cgs(Ad, torch.zeros(n, dtype=torch.float64, device="cuda"), _dev(B[:, 0].copy()), Md, 12, tol)
     assert i1 == its[0] and f1 == flags[0] and _rel(x1.cpu().numpy(), Xh[:, 0]) <= 1e-12

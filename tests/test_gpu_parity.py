@@ -7,6 +7,7 @@ import torch
 
 from oracle import toeplitz_oracle as O
 from oracle import build_oracle as OC
+import parity_tools as PT
 
 pytestmark = pytest.mark.gpu
 
@@ -183,7 +184,10 @@ def test_circulant_family(tb, dtype, n):
     """src/linearalgebra.jl:183-315: power-of-two sizes (direct plan, incl. a two-level size) and the
     reference's own test sizes 5, 6, 101, 2000 (chirp-z plan)."""
     rng = np.random.default_rng(n + 7)
-    tol = tol_of(dtype) * 10
+    tag = "circulant n=%d %s " % (n, np.dtype(dtype).name)
+
+    def chk(name, got, ref, cond=1.0):
+        PT.check(tag + name, got, ref, dtype, cond)
     v = p(0.9, n, dtype)
     v2 = (rng.random(n) + 0.5).astype(dtype)
     Co, Cd = O.Circulant(v), tb.Circulant(dev(v))
@@ -191,35 +195,39 @@ def test_circulant_family(tb, dtype, n):
     Fo, Fd = O.factorize(Co), tb.factorize(Cd)
     assert Fd.size() == (n, n) and Fd.size(1) == n
     # eigvals: DFT order, fft(C.vc) == spectrum (test/runtests.jl:543)
-    assert rel(host(tb.eigvals(Cd)), np.fft.fft(v.astype(np.complex128))) <= tol
+    lam = np.fft.fft(v.astype(np.complex128))
+    lam2 = np.fft.fft(v2.astype(np.complex128))
+    kC, kC2 = PT.cond_spectrum(lam), PT.cond_spectrum(lam2)      # 2-norm condition numbers of C and C2 (normal matrices)
+    chk("eigvals", host(tb.eigvals(Cd)), lam)
     # ldiv! vector / matrix / 3-arg
     B = (rng.standard_normal((n, 4)) + (1j * rng.standard_normal((n, 4)) if np.dtype(dtype).kind == "c" else 0)).astype(dtype)
     Bo = np.asfortranarray(B.copy())
     O.ldiv_mat(Co, Bo, O.circ_ldiv)
     Bd = devmat(B.copy())
     tb.ldiv_(Cd, Bd)
-    assert rel(host(Bd), Bo) <= tol
+    chk("ldiv! matrix", host(Bd), Bo, kC)
     xo = torch.zeros(n, dtype=Bd.dtype, device="cuda")
     tb.circ_ldiv_(Fd, dev(B[:, 0].copy()), out=xo)
-    assert rel(host(xo), Bo[:, 0]) <= tol
-    assert rel(host(tb.ldiv(Cd, dev(B[:, 1].copy()))), Bo[:, 1]) <= tol
+    chk("ldiv! 3-arg", host(xo), Bo[:, 0], kC)
+    chk("ldiv vector", host(tb.ldiv(Cd, dev(B[:, 1].copy()))), Bo[:, 1], kC)
     # inv / pinv / sqrt / det / products
-    assert rel(host(tb.inv(Cd).vc), O.circ_inv(Co).vc) <= tol
-    assert rel(host(tb.pinv(Cd).vc), O.circ_pinv(Co).vc) <= tol
-    assert rel(host(tb.sqrt(C2d).vc), O.circ_sqrt(C2o).vc) <= tol
+    chk("inv", host(tb.inv(Cd).vc), O.circ_inv(Co).vc, kC)
+    chk("pinv", host(tb.pinv(Cd).vc), O.circ_pinv(Co).vc, kC)
+    chk("sqrt", host(tb.sqrt(C2d).vc), O.circ_sqrt(C2o).vc, np.sqrt(kC2))
     for ta in (False, True):
         for tbb in (False, True):
             Ao_ = Fo.adjoint() if ta else Fo
             Bo_ = O.factorize(C2o).adjoint() if tbb else O.factorize(C2o)
             Ad_ = tb.adjoint(Fd) if ta else Fd
             Bd_ = tb.adjoint(tb.factorize(C2d)) if tbb else C2d
-            assert rel(host(tb.circ_mul(Ad_, Bd_).vc), O.circ_mul(Ao_, Bo_).vc) <= tol
+            chk("A*B adj=%d%d" % (ta, tbb), host(tb.circ_mul(Ad_, Bd_).vc), O.circ_mul(Ao_, Bo_).vc)
     # issue #47: inv(F) * C ~ I
     e = rng.random(n).astype(np.zeros(1, dtype).real.dtype)
     Iv = tb.circ_mul(tb.inv(Fd), Cd)
-    assert rel(host(tb.mul(Iv, dev(e))), e) <= tol
+    chk("inv(F)*C ~ I", host(tb.mul(Iv, dev(e))), e, kC)
     if n <= 64:
-        assert rel(host(tb.det(C2d)).item(), O.circ_det(C2o)) <= (1e-3 if np.dtype(dtype) == np.complex64 else 1e-10)
+        # a determinant is a product of n eigenvalues: relative error <= n * (error of one eigenvalue)
+        chk("det", host(tb.det(C2d)).item(), O.circ_det(C2o), float(n))
 
 
 def test_circulant_identity_issue73(tb):
@@ -268,15 +276,17 @@ def test_levinson_reference_kernels(tb):
         a = a.copy()
         a[0] = 1
         r = a[1:]
-        assert rel(host(tb.durbin(dev(r))), O.durbin(r)) <= 1e-10
+        T = O.SymmetricToeplitz(np.concatenate([[1.0], r[:-1]])).dense()
+        kT = PT.cond2(T)                                  # exp(-|x|) and exp(-x^2)/2 kernels: cond up to ~1e3
+        PT.check("durbin n=8 kernel", host(tb.durbin(dev(r))), O.durbin(r), np.float64, kT)
         b = g.standard_normal(n)
-        assert rel(host(tb.levinson(dev(r[:-1].copy()), dev(b))), O.levinson(r[:-1], b)) <= 1e-10
+        PT.check("levinson n=8 kernel", host(tb.levinson(dev(r[:-1].copy()), dev(b))), O.levinson(r[:-1], b), np.float64, kT)
         TS = 2.1 * np.concatenate([[1.0], r[:-1]])
         xs = host(tb.levinson(tb.SymmetricToeplitz(dev(TS)), dev(b)))
-        assert rel(xs, np.linalg.solve(O.SymmetricToeplitz(TS).dense(), b)) <= 1e-9
+        PT.check("levinson(T, b) vs dense solve", xs, np.linalg.solve(O.SymmetricToeplitz(TS).dense(), b), np.float64, kT)
         Bm = g.standard_normal((n, 3))
         Xs = host(tb.levinson(tb.SymmetricToeplitz(dev(TS)), devmat(Bm)))
-        assert rel(Xs, np.linalg.solve(O.SymmetricToeplitz(TS).dense(), Bm)) <= 1e-9
+        PT.check("levinson(T, B) vs dense solve", Xs, np.linalg.solve(O.SymmetricToeplitz(TS).dense(), Bm), np.float64, kT)
 
 
 def test_levinson_float32(tb):
@@ -302,14 +312,20 @@ def test_cgs_matches_oracle(tb, dtype):
     xd, ed, itd, fd = tb.cgs(Ad, torch.zeros(n, dtype=dev(b).dtype, device="cuda"), dev(b),
                              tb.factorize(tb.strang(Ad)), 50, tol)
     assert fd == fo and abs(itd - ito) <= 1
-    assert rel(host(xd), xo) <= (1e-10 if np.dtype(dtype) != np.complex64 else 1e-4)
+    kA = PT.cond2(Ao.dense())                              # KMS(0.5): ~9
+    # both runs stop at a relative residual <= tol: the solutions agree to cond * (res_o + res_d)
+    PT.check("cgs to tolerance", host(xd), xo, dtype, kA, extra=2.0 * kA * (eo + ed))
     assert ed <= max(10 * eo, tol)
-    # fixed iteration count (no convergence -> flag 1) keeps the iterates aligned
+    # fixed iteration count (no convergence -> flag 1): the iteration keeps running after the residual has reached
+    # its rounding floor, so the iterates agree to cond * (floor of the residual), measured on both sides
     xo2, eo2, ito2, fo2 = O.cgs(Ao, np.zeros(n, dtype), b.copy(), O.factorize(O.strang(Ao)), 3, 0.0)
     xd2, ed2, itd2, fd2 = tb.cgs(Ad, torch.zeros(n, dtype=dev(b).dtype, device="cuda"), dev(b),
                                  tb.factorize(tb.strang(Ad)), 3, 0.0)
     assert (itd2, fd2) == (ito2, fo2) == (3, 1)
-    assert rel(host(xd2), xo2) <= (1e-9 if np.dtype(dtype) != np.complex64 else 1e-3)
+    D = Ao.dense().astype(np.complex128)
+    true_o = np.linalg.norm(b - D @ xo2) / np.linalg.norm(b)
+    true_d = np.linalg.norm(b - D @ host(xd2)) / np.linalg.norm(b)
+    PT.check("cgs 3 iterations", host(xd2), xo2, dtype, kA, extra=2.0 * kA * (true_o + true_d))
 
 
 def test_strang_chan(tb):
@@ -396,9 +412,10 @@ def test_bluestein_factorization_products(tb):
             Y0 = rng.standard_normal((n, 3)).astype(dtype)
             Yd = devmat(Y0.copy())
             tb.mul_(Yd, F, devmat(X), 2.0, -0.5)
-            ref = 2.0 * (Co.dense() @ X) - 0.5 * Y0
-            assert rel(host(Yd), ref) <= tol_of(dtype) * 10
-            assert rel(host(tb.mul(F, dev(X[:, 0].copy()))), Co.dense() @ X[:, 0]) <= tol_of(dtype) * 10
+            wide = np.complex128 if np.dtype(dtype).kind == "c" else np.float64
+            Dw, Xw = Co.dense().astype(wide), X.astype(wide)             # the definition, evaluated in double
+            PT.check("bluestein n=%d mul! alpha/beta" % n, host(Yd), 2.0 * (Dw @ Xw) - 0.5 * Y0.astype(wide), dtype)
+            PT.check("bluestein n=%d mul vector" % n, host(tb.mul(F, dev(X[:, 0].copy()))), Dw @ Xw[:, 0], dtype)
 
 
 def test_edge_shapes(tb):
@@ -445,12 +462,13 @@ def test_triangular_inverse(tb, n):
         if np.dtype(dtype).kind == "c":
             v = v * np.exp(0.3j * np.arange(n))
         ref = O.tri_inv_lower(v)
-        assert rel(host(tb.inv(tb.LowerTriangularToeplitz(dev(v))).v), ref) <= 1e-11
+        kL = PT.cond2(O.LowerTriangularToeplitz(v).dense()) if n <= 700 else 9.0      # |1 + 0.5 z/(1-0.7z)| on |z|=1: cond < 9
+        PT.check("tri inv lower n=%d" % n, host(tb.inv(tb.LowerTriangularToeplitz(dev(v))).v), ref, dtype, kL)
         Ui = tb.inv(tb.UpperTriangularToeplitz(dev(v)))
         assert isinstance(Ui, tb.UpperTriangularToeplitz)
         if n <= 700:
             dense = np.linalg.inv(O.UpperTriangularToeplitz(v).dense())
-            assert rel(O.UpperTriangularToeplitz(host(Ui.v)).dense(), dense) <= 1e-10
+            PT.check("tri inv upper n=%d" % n, O.UpperTriangularToeplitz(host(Ui.v)).dense(), dense, dtype, kL)
 
 
 @pytest.mark.parametrize("n", [1, 2, 9, 100, 513, 1500])
@@ -460,13 +478,14 @@ def test_trench(tb, n):
     a = np.concatenate([[1.0], rng.random(n - 1) / max(n, 2)])
     T = O.SymmetricToeplitz(a)
     B = host(tb.trench(tb.SymmetricToeplitz(dev(a))))
-    assert rel(B, np.linalg.inv(T.dense())) <= 1e-10
+    kT = PT.cond2(T.dense())
+    PT.check("trench n=%d vs dense inv" % n, B, np.linalg.inv(T.dense()), np.float64, kT)
     if 2 <= n <= 100:
-        assert rel(B, O.trench(T)) <= 1e-12
+        PT.check("trench n=%d vs oracle" % n, B, O.trench(T), np.float64, kT)
     TS = O.SymmetricToeplitz(2.3 * a)
-    assert rel(host(tb.trench(tb.SymmetricToeplitz(dev(2.3 * a)))), np.linalg.inv(TS.dense())) <= 1e-10
+    PT.check("trench scaled n=%d" % n, host(tb.trench(tb.SymmetricToeplitz(dev(2.3 * a)))), np.linalg.inv(TS.dense()), np.float64, kT)
     if n >= 2:
-        assert rel(host(tb.trench(dev(a[1:].copy()))), np.linalg.inv(T.dense())) <= 1e-10
+        PT.check("trench(r) n=%d" % n, host(tb.trench(dev(a[1:].copy()))), np.linalg.inv(T.dense()), np.float64, kT)
 
 
 def test_mul_host_pageable_and_complex(tb):
@@ -494,7 +513,8 @@ def test_levinson_multirhs_shared_recursion(tb, n):
     X = host(tb.levinson(tb.SymmetricToeplitz(dev(a)), devmat(Bm)))
     ref = np.stack([OC.c_levinson_sym(a, Bm[:, j]) for j in range(Bm.shape[1])], axis=1)
     assert rel(X, ref) <= TOL64
-    assert rel(X, np.linalg.solve(O.SymmetricToeplitz(a).dense(), Bm)) <= 1e-10
+    D = O.SymmetricToeplitz(a).dense()
+    PT.check("levinson multirhs n=%d vs dense solve" % n, X, np.linalg.solve(D, Bm), np.float64, PT.cond2(D))
 
 
 @pytest.mark.parametrize("n", [1000, 70000])

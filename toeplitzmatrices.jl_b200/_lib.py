@@ -21,7 +21,7 @@ EXPORTS = [
     "tb200_circ_spectrum", "tb200_circ_map", "tb200_circ_mul", "tb200_circ_to_vc",
     "tb200_precond_vector", "tb200_levinson_batched", "tb200_durbin_batched", "tb200_cgs", "tb200_cg",
     "tb200_factorize_empty", "tb200_spectrum_buffer", "tb200_launch_count", "tb200_set_option",
-    "tb200_pass_times", "tb200_trench", "tb200_tri_smallinv", "tb200_levinson_multirhs",
+    "tb200_pass_times", "tb200_pass_times_ex", "tb200_trench", "tb200_tri_smallinv", "tb200_levinson_multirhs",
     "tb200_cgs_batched", "tb200_cg_batched", "tb200_spectrum_ready",
     "tb200_comm_init", "tb200_comm_unique_id", "tb200_comm_init_rank", "tb200_comm_size", "tb200_bcast_spectrum",
     "tb200_comm_destroy",
@@ -91,6 +91,7 @@ def lib() -> ctypes.CDLL:
         "tb200_comm_destroy": [vp],
         "tb200_set_option": [ctypes.c_char_p, i64],
         "tb200_pass_times": [pd, pi64],
+        "tb200_pass_times_ex": [pd, pi64, ctypes.c_int],
         "tb200_trench": [ci, i64, vp, vp, i64, dbl, vp],
         "tb200_tri_smallinv": [ci, i64, vp, vp, vp],
         "tb200_levinson_multirhs": [ci, i64, i64, vp, vp, i64, vp, i64, vp],

@@ -878,8 +878,8 @@ def set_option(name: str, value: int) -> None:
 
 def pass_times():
     """Drain the per-pass CUDA-event timers: ({name: ms}, {name: launches})."""
-    ms = (ctypes.c_double * 4)()
-    cnt = (ctypes.c_int64 * 4)()
-    check(L.lib().tb200_pass_times(ms, cnt))
-    names = ("cols_A", "rows_B", "cols_C", "rows_single")
+    ms = (ctypes.c_double * 5)()
+    cnt = (ctypes.c_int64 * 5)()
+    check(L.lib().tb200_pass_times_ex(ms, cnt, 5))
+    names = ("cols_A", "rows_B", "cols_C", "rows_single", "cols_CA")
     return {k: ms[i] for i, k in enumerate(names)}, {k: cnt[i] for i, k in enumerate(names)}

@@ -60,15 +60,19 @@ def build_variant(tag: str, defines) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + ["-D" + d for d in defines]
 
+    sources = list(SOURCES)
+    if any(d.startswith("TB_EXP_CA") for d in defines):
+        sources.append(os.path.join("experiments", "cols_ca.cu"))       # fused pass C + pass A launches (option ca_fuse)
+
     def one(src):
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, os.path.basename(src).replace(".cu", ".o"))
         r = subprocess.run([_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(r.stderr)
         return obj
 
     with cf.ThreadPoolExecutor(max_workers=8) as ex:
-        objs = list(ex.map(one, SOURCES))
+        objs = list(ex.map(one, sources))
     lib = os.path.join(LIBDIR, "libtoeplitz_b200_%s.so" % tag)
     r = subprocess.run([_nvcc(), "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
                         "-Xcompiler", "-fPIC", "-cudart", "static"], capture_output=True, text=True)

@@ -32,6 +32,7 @@ static std::atomic<long long> g_group_bytes{48ll << 20};   // two-level scratch 
 static std::atomic<long long> g_host_chunk_bytes{256ll << 20};
 static std::atomic<long long> g_krylov_work_bytes{16ll << 30};   // work-vector budget of the batched cgs / cg (columns per chunk)
 static std::atomic<int> g_time_passes{0};
+static std::atomic<int> g_ca_fuse{0};            // 1: pass C of a group + pass A of the next one on its stream as one launch; 2: + async x tile
 static std::atomic<int> g_l2_persist_mb{64};     // persisting-L2 carve-out for the two-level workspaces (0 = off); +4 % on config 2
 static std::atomic<int> g_tma{0};                // TMA-staged strided passes (tma_cols.cuh) where eligible; measured, see DESIGN.md
 extern int g_lev_gen;                            // levinson.cu
@@ -44,7 +45,7 @@ static std::atomic<int> g_single_max_f64{13}, g_single_max_f32{14};   // longest
 // launching stream around every pass while "time_passes" is on.
 struct PassEvents { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; };
 static std::mutex g_pass_mutex;
-static PassEvents g_pass[4];      // 0 = cols A, 1 = rows B, 2 = cols C, 3 = single-kernel rows
+static PassEvents g_pass[5];      // 0 = cols A, 1 = rows B, 2 = cols C, 3 = single-kernel rows, 4 = fused cols C+A
 
 struct PassTimer {
     int which; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr; bool on;
@@ -413,6 +414,18 @@ static int make_plan(tb200_fact* h) {
 // Persisting-L2 access window on a stream's workspace: its lines are kept (hitProp persisting) while the streamed
 // x / y columns of the same kernels pass through the rest of the cache -- the workspace is written by pass A,
 // rewritten by pass B and read by pass C, and must not be evicted in between by 16 MiB of x and y per column pair.
+static std::atomic<long long> g_l2_applied[64];     // persisting-L2 carve-out currently set on each device (bytes)
+// The carve-out is a device-wide limit: while it is set, normal and streaming accesses of EVERY kernel lose that part
+// of L2 (config 3 with 2 x 64 MiB workspaces: 9.3 k -> 6.4 k solves/s, config 5a 0.53 -> 0.69 ms, probe 5).  Products
+// that do not use the window hand it back, together with the lines still tagged persisting.
+static void release_l2_carveout() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_l2_applied[dev & 63].exchange(0) != 0) {
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    }
+}
 static void apply_l2_window(cudaStream_t st, void* base, size_t bytes, int nwindows) {
     const int mb = g_l2_persist_mb.load();
     cudaStreamAttrValue v;
@@ -423,8 +436,7 @@ static void apply_l2_window(cudaStream_t st, void* base, size_t bytes, int nwind
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
         size_t want = std::min<size_t>((size_t)mb << 20, (size_t)std::max(max_persist, 0));
-        static std::atomic<long long> applied[64];
-        if (applied[dev & 63].exchange((long long)want) != (long long)want) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        if (g_l2_applied[dev & 63].exchange((long long)want) != (long long)want) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
         const size_t wbytes = std::min<size_t>(bytes, (size_t)std::max(max_window, 0));
         const double share = (double)want / (double)std::max<size_t>(wbytes * (size_t)std::max(nwindows, 1), 1);
         v.accessPolicyWindow.base_ptr = base;
@@ -555,9 +567,7 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     // 15-30 % (profiles/experiments_r02.md)
     const size_t ws_in_flight = (size_t)nstr * (size_t)G * Np * sizeof(cx<R>);
     const bool l2win = g_l2_persist_mb.load() > 0 && ws_in_flight <= ((size_t)g_l2_persist_mb.load() << 20);
-    static std::atomic<bool> persisting_lines{false};        // lines tagged persisting may still sit in the carve-out
-    if (l2win) persisting_lines = true;
-    else if (persisting_lines.exchange(false)) cudaCtxResetPersistingL2Cache();   // give the carve-out back to normal traffic
+    if (!l2win) release_l2_carveout();      // a carve-out left behind by a smaller product halves the L2 everyone else sees
     for (int i = 0; i < nstr; ++i) {
         if (l2win) { apply_l2_window(stream_of[i], scratch_of[i], (size_t)G * Np * sizeof(cx<R>), nstr); w->win_set[i] = true; }
         else if (w->win_set[i]) { apply_l2_window(stream_of[i], nullptr, 0, 1); w->win_set[i] = false; }
@@ -598,6 +608,44 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
             }
         }
     }
+    // arguments of the strided passes of the group that starts at FFT slot f0 and holds g slots
+    auto args_A = [&](long long f0, long long g, cx<R>* scratch) {
+        ConvArgs<R> pa = a;
+        pa.scratch = scratch;
+        pa.nfft = g;
+        pa.tw = tw_cols;
+        pa.ncols = c.ncols - f0 * cols_per_fft;
+        if (c.colmap) pa.colmap = c.colmap + f0 * cols_per_fft;
+        else pa.x = reinterpret_cast<const char*>(c.x) + (size_t)f0 * cols_per_fft * c.ldx * in_esz;
+        return pa;
+    };
+    auto args_C = [&](long long f0, long long g, cx<R>* scratch) {
+        ConvArgs<R> pc = a;
+        pc.scratch = scratch;
+        pc.nfft = g;
+        pc.tw = tw_cols;
+        pc.ncols = c.ncols - f0 * cols_per_fft;
+        if (c.colmap) pc.colmap = c.colmap + f0 * cols_per_fft;
+        else {
+            pc.y = reinterpret_cast<char*>(c.y) + (size_t)f0 * cols_per_fft * c.ldy * out_esz;
+            if (c.col_alpha) pc.col_alpha = c.col_alpha + f0 * cols_per_fft * c.col_alpha_stride;   // indexed by user column
+        }
+        return pc;
+    };
+    // Fused C+A (k_colsCA): the last pass of a group and the first pass of the next group on the same stream / workspace
+    // run as one launch.  Both sides must agree on the half-padding variant.
+    const long long halfN = Np / 2;
+    const bool half_ok = g_prune_half && le_of<R>() == 4 && h->log2l1 >= 4;
+    const bool halfA = half_ok && c.n_in <= halfN && c.x_mode != IO_SPEC;
+    const bool halfC = half_ok && c.m_out <= halfN;
+#ifdef TB_EXP_CA
+    const bool fuse = g_ca_fuse.load() && c.do_fwd && c.do_inv && !tmaA && !tmaC && halfA == halfC &&
+                      c.nfft > (long long)nstr * G && cols_ca_supported<R>(h->log2l1, h->ta);
+    const bool stage = fuse && g_ca_fuse.load() >= 2 && halfA && (c.x_mode == IO_PAIR || c.x_mode == IO_REAL);
+#else
+    const bool fuse = false;        // experiment build only (csrc/experiments/ca_kernels.cuh): measured slower
+    (void)halfA; (void)halfC;
+#endif
     long long group_index = 0;
     for (long long f0 = 0; f0 < c.nfft; f0 += G, ++group_index) {
         const long long g = std::min(G, c.nfft - f0);
@@ -606,20 +654,25 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
         a.scratch = scratch;
         // pass A
         if (c.do_fwd) {
-            ConvArgs<R> pa = a;
-            pa.nfft = g;
-            pa.tw = tw_cols;
-            pa.ncols = c.ncols - f0 * cols_per_fft;
             if (c.x_mode == IO_SPEC) return set_error(TB200_BAD_ARG, "internal: IO_SPEC input with forward transform");
-            if (c.colmap) pa.colmap = c.colmap + f0 * cols_per_fft;
-            else pa.x = reinterpret_cast<const char*>(c.x) + (size_t)f0 * cols_per_fft * c.ldx * in_esz;
+            const ConvArgs<R> pa = args_A(f0, g, scratch);
             count_launch();
-            PassTimer pt(0, s);
-            if (tmaA) {
-                tlA.col0 = (int)(f0 * cols_per_fft);
-                TB_CUDA(launch_colsA_tma<R>(h->log2l1, h->ta, pa, &xmap, tlA, s), "k_colsA_tma");
-            } else
-            TB_CUDA(launch_colsA<R>(h->log2l1, h->ta, pa, s), "k_colsA");
+            if (fuse && group_index >= nstr) {       // with pass C of the previous group of this stream (always a full group)
+                const ConvArgs<R> pc = args_C(f0 - (long long)nstr * G, G, scratch);
+                PassTimer pt(4, s);
+#ifdef TB_EXP_CA
+                TB_CUDA(launch_colsCA<R>(h->log2l1, h->ta, pc, pa, halfA, stage, s), "k_colsCA");
+#else
+                (void)pc;
+#endif
+            } else {
+                PassTimer pt(0, s);
+                if (tmaA) {
+                    tlA.col0 = (int)(f0 * cols_per_fft);
+                    TB_CUDA(launch_colsA_tma<R>(h->log2l1, h->ta, pa, &xmap, tlA, s), "k_colsA_tma");
+                } else
+                TB_CUDA(launch_colsA<R>(h->log2l1, h->ta, pa, s), "k_colsA");
+            }
         }
         // pass B: rows of the scratch, in place
         {
@@ -643,17 +696,9 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
             PassTimer pt(1, s);
             TB_CUDA(launch_rows<R>(h->log2l2, pb, num_sms(), s), "k_rows (pass B)");
         }
-        // pass C
-        if (c.do_inv) {
-            ConvArgs<R> pc = a;
-            pc.nfft = g;
-            pc.tw = tw_cols;
-            pc.ncols = c.ncols - f0 * cols_per_fft;
-            if (c.colmap) pc.colmap = c.colmap + f0 * cols_per_fft;
-            else {
-                pc.y = reinterpret_cast<char*>(c.y) + (size_t)f0 * cols_per_fft * c.ldy * out_esz;
-                if (c.col_alpha) pc.col_alpha = c.col_alpha + f0 * cols_per_fft * c.col_alpha_stride;   // indexed by user column
-            }
+        // pass C (deferred into the next group's fused launch when this stream has one)
+        if (c.do_inv && !(fuse && f0 + (long long)nstr * G < c.nfft)) {
+            const ConvArgs<R> pc = args_C(f0, g, scratch);
             count_launch();
             PassTimer pt(2, s);
             if (tmaC) {
@@ -837,19 +882,31 @@ const char* tb200_version(void) { return "toeplitz_b200 0.1.0 (sm_100a)"; }
 const char* tb200_last_error(void) { return g_err; }
 int64_t tb200_launch_count(void) { return g_launches.load(); }
 
-int tb200_pass_times(double ms[4], int64_t counts[4]) {
-    if (!ms || !counts) return set_error(TB200_BAD_ARG, "NULL argument");
+int tb200_pass_times_ex(double* ms, int64_t* counts, int n) {
+    if (!ms || !counts || n < 1) return set_error(TB200_BAD_ARG, "NULL argument");
     std::lock_guard<std::mutex> lock(g_pass_mutex);
-    for (int w = 0; w < 4; ++w) {
-        ms[w] = 0; counts[w] = 0;
+    for (int w = 0; w < 5; ++w) {
+        double tot = 0; int64_t cnt = 0;
         for (auto& pr : g_pass[w].ev) {
             float t = 0;
             cudaEventSynchronize(pr.second);
-            if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) { ms[w] += t; counts[w] += 1; }
+            if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) { tot += t; cnt += 1; }
             cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
         }
         g_pass[w].ev.clear();
+        if (w < n) { ms[w] = tot; counts[w] = cnt; }
+        else { ms[n - 1] += tot; counts[n - 1] += cnt; }       // a shorter array folds the rest into its last entry
     }
+    return TB200_OK;
+}
+
+int tb200_pass_times(double ms[4], int64_t counts[4]) {
+    // four-entry form: the fused C+A launches (entry 4 of tb200_pass_times_ex) are reported with pass C
+    double m5[5]; int64_t c5[5];
+    TB_TRY(tb200_pass_times_ex(m5, c5, 5));
+    if (!ms || !counts) return set_error(TB200_BAD_ARG, "NULL argument");
+    for (int w = 0; w < 4; ++w) { ms[w] = m5[w]; counts[w] = c5[w]; }
+    ms[2] += m5[4]; counts[2] += c5[4];
     return TB200_OK;
 }
 
@@ -861,6 +918,7 @@ int tb200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "krylov_work_bytes")) { g_krylov_work_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "host_chunk_bytes")) { g_host_chunk_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "time_passes")) { g_time_passes = value ? 1 : 0; return TB200_OK; }
+    if (!strcmp(name, "ca_fuse")) { g_ca_fuse = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 2); return TB200_OK; }
     if (!strcmp(name, "l2_persist_mb")) { g_l2_persist_mb = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 1024); return TB200_OK; }
     if (!strcmp(name, "lev_gen")) { g_lev_gen = (int)(value & 1); return TB200_OK; }
     if (!strcmp(name, "prune_half")) { g_prune_half = value ? 1 : 0; return TB200_OK; }

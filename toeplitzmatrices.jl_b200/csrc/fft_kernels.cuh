@@ -54,6 +54,13 @@ __device__ __forceinline__ void level_twiddles(const ConvArgs<R>& p, int t, int 
 
 // ---- per-slot input / output views: the embedding (zero pad, Hankel reversal), the packing of
 // ---- two real columns as re + i*im, and the alpha/beta/real-part epilogue are fused here ----
+__device__ __forceinline__ void cp_async_elem(double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
 template <typename R>
 struct InView {
     const R* re; const R* im; const cx<R>* c; int mode; int n_in; int rev;
@@ -68,6 +75,14 @@ struct InView {
             re = base + (cm ? (long long)cm[2 * f] : 2 * f) * p.ldx;
             im = (2 * f + 1 < p.ncols) ? base + (cm ? (long long)cm[2 * f + 1] : 2 * f + 1) * p.ldx : nullptr;
         }
+    }
+    // real modes only: start the asynchronous copy (LDGSTS) of logical element idx into the caller's own staging slots
+    __device__ __forceinline__ void stage_real(int idx, R* dre, R* dim_) const {
+        if (idx >= n_in) { *dre = 0; *dim_ = 0; return; }
+        const int src = rev ? (n_in - 1 - idx) : idx;
+        cp_async_elem(dre, re + src);
+        if (im) cp_async_elem(dim_, im + src);
+        else *dim_ = 0;
     }
     __device__ __forceinline__ cx<R> load(int idx) const {
         if (idx >= n_in) return mk<R>(0, 0);

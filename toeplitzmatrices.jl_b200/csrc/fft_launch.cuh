@@ -13,6 +13,9 @@ template <typename R> constexpr int rows_ts(int log2l) {
 template <typename R> cudaError_t launch_rows(int log2l, const ConvArgs<R>& a, int num_sms, cudaStream_t s);
 template <typename R> cudaError_t launch_colsA(int log2l1, int ta, const ConvArgs<R>& a, cudaStream_t s);
 template <typename R> cudaError_t launch_colsC(int log2l1, int ta, const ConvArgs<R>& a, cudaStream_t s);
+// fused pass C (pc) + pass A of the next group on the same workspace (pa); experiments/cols_ca.cu, TB_EXP_CA builds only
+template <typename R> cudaError_t launch_colsCA(int log2l1, int ta, const ConvArgs<R>& pc, const ConvArgs<R>& pa, bool half, bool stage, cudaStream_t s);
+template <typename R> bool cols_ca_supported(int log2l1, int ta);
 
 template <typename R, int LOG2L>
 cudaError_t launch_rows_one(const ConvArgs<R>& a, int num_sms, cudaStream_t s) {
