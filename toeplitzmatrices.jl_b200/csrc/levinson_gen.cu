@@ -25,6 +25,8 @@
 // Start:  A = r (r[1..]), B = (1, r[1], r[2], ...), X = -b.
 //
 // Register layout as in levinson_kernels.cuh (blocked-cyclic, phase-indexed shifting vector).
+// (A software-pipelined step -- slot k+1 updated and broadcast first, 1/beta_{k+1} started beside the FMAs -- measured
+// the same 12.5 M solves/s: the kernel is throttled by the FP64 pipe, not by its dependent chain; profiles/experiments_r02.md.)
 #include "levinson_kernels.cuh"
 
 namespace tb {
@@ -32,57 +34,39 @@ namespace tb {
 template <typename R, int S, bool DURBIN>
 struct GenState {
     R a[S * LB], b[S * LB], x[DURBIN ? 1 : S * LB];
-    R alpha, mu, beta;        // alpha_k, mu_k of the step about to run; beta_k
+    R alpha, beta;
 };
 
-// One step k = SC*SPAN + lb*4 + J (J, SC compile time).  B has been shifted k times: phase J.
-// Software-pipelined across steps: the step receives alpha_k, mu_k and hands alpha_{k+1}, mu_{k+1} to the next one.
-// What the next step waits for is ONE slot, k+1, so that slot is updated first and broadcast while the other
-// 3 * 4S - 2 FMAs of this step issue; the beta -> 1/beta chain of step k+1 depends on alpha_k only and runs beside them
-// as well.  The dependent chain per step shrinks to FMA -> shuffle -> multiply.
-// LAST: the final step of levinson! (k = n-1) applies mu only (:114 `if k < n-1`).
+// one step k = SC*SPAN + lb*4 + J (J, SC compile time).  B has been shifted k times: phase J.
+// LAST: the final step of levinson! (k = n-1) needs mu only (:114 `if k < n-1`).
 template <typename R, int S, int SC, int J, bool DURBIN, bool LAST, int P>
 __device__ __forceinline__ void gen_step(GenState<R, S, DURBIN>& st, int lane, int lb) {
     constexpr int N = S * LB;
     constexpr int PH = J;
     const int sub = lane & (P - 1);
-    const R alpha = st.alpha, mu = st.mu;
-    if constexpr (LAST) {
+    const int owner = (lane & ~(P - 1)) | lb;
+    st.beta *= ((R)1 - st.alpha * st.alpha);          // alpha = 0 before the first step: beta_0 = 1
+    const R ibeta = fast_rcp2(st.beta);
+    const R ak = __shfl_sync(0xffffffffu, st.a[SC * LB + J], owner);
+    if constexpr (!DURBIN) {
+        const R xk = __shfl_sync(0xffffffffu, st.x[SC * LB + J], owner);
+        const R mu = -xk * ibeta;
 #pragma unroll
         for (int i = 0; i < N; ++i) st.x[i] = fma(mu, st.b[phys(i, PH)], st.x[i]);
         if (sub == lb) st.x[SC * LB + J] = mu;
-        return;
     }
-    // 1/beta_{k+1}: beta *= 1 - alpha^2 (:106)
-    st.beta *= ((R)1 - alpha * alpha);
-    const R ibn = fast_rcp2(st.beta);
-    // slot k+1: same lane, next register (J < 3); first register of the next lane's block (J == 3), which is the first
-    // register of the next super-row in lane 0 when this was the last lane
-    constexpr int RN = SC * LB + ((J + 1) & (LB - 1));
-    constexpr int RW = (SC + 1 < S) ? (SC + 1) * LB : SC * LB;
-    const bool wrap = (J == LB - 1) && (lb == P - 1);
-    const int owner_next = (lane & ~(P - 1)) | ((J == LB - 1) ? ((lb + 1) & (P - 1)) : lb);
-    const R bn = (J == LB - 1 && wrap) ? st.b[phys(RW, PH)] : st.b[phys(RN, PH)];
-    const R an = fma(alpha, bn, (J == LB - 1 && wrap) ? st.a[RW] : st.a[RN]);
-    const R ak1 = __shfl_sync(0xffffffffu, an, owner_next);
-    R xk1 = 0;
-    if constexpr (!DURBIN) {
-        const R xn = fma(mu, bn, (J == LB - 1 && wrap) ? st.x[RW] : st.x[RN]);
-        xk1 = __shfl_sync(0xffffffffu, xn, owner_next);
+    if constexpr (!LAST) {
+        const R alpha = -ak * ibeta;
+        st.alpha = alpha;
 #pragma unroll
-        for (int i = 0; i < N; ++i) st.x[i] = (J < LB - 1 && i == RN) ? xn : fma(mu, st.b[phys(i, PH)], st.x[i]);
-        if (sub == lb) st.x[SC * LB + J] = mu;
+        for (int i = 0; i < N; ++i) {
+            const R ao = st.a[i], bo = st.b[phys(i, PH)];
+            st.a[i] = fma(alpha, bo, ao);
+            st.b[phys(i, PH)] = fma(alpha, ao, bo);
+        }
+        if (sub == lb) st.a[SC * LB + J] = alpha;
+        shift_up<R, S, PH, P>(st.b, alpha, lane);
     }
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const R ao = st.a[i], bo = st.b[phys(i, PH)];
-        st.a[i] = (J < LB - 1 && i == RN) ? an : fma(alpha, bo, ao);
-        st.b[phys(i, PH)] = fma(alpha, ao, bo);
-    }
-    if (sub == lb) st.a[SC * LB + J] = alpha;
-    shift_up<R, S, PH, P>(st.b, alpha, lane);
-    st.alpha = -ak1 * ibn;
-    if constexpr (!DURBIN) st.mu = -xk1 * ibn;
 }
 
 template <typename R, int S, int SC, bool DURBIN, int P>
@@ -159,8 +143,7 @@ k_levinson_gen(int64_t n64, int64_t nsys, const R* __restrict__ Rm, int64_t ldr,
             st.b[sr * LB + j] = (s < n) ? r_s[s] : (R)0;
             if constexpr (!DURBIN) st.x[sr * LB + j] = (s < n) ? -bcol[s] : (R)0;
         }
-    st.alpha = -r_s[1];                       // alpha_0 = -r[1], mu_0 = b[1], beta_0 = 1 (:102-104)
-    st.mu = DURBIN ? (R)0 : bcol[0];
+    st.alpha = 0;
     st.beta = (R)1;
     gen_superrows<R, S, 0, DURBIN, P>(st, n, lane);
 
