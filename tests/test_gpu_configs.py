@@ -200,3 +200,29 @@ def test_levinson_durbin_both_kernel_families(tb, n, dtype):
         assert rel(X.cpu().numpy(), xo) <= tol, ("levinson", gen)
         assert rel(Y.cpu().numpy(), yo) <= tol, ("durbin", gen)
         assert rel(Xd.cpu().numpy(), xo / diag.astype(np.float64)) <= tol, ("levinson diag", gen)
+
+
+@pytest.mark.parametrize("n,dtype", [(2100, "float64"), (5000, "float64"), (6400, "float64"), (7000, "float64"), (20000, "float64"),
+                                     (12000, "float32"), (30000, "float32")])
+def test_levinson_durbin_any_order(tb, n, dtype):
+    """Orders beyond the register kernels: one CTA per system in generator form, vectors in shared memory (n <= 6400 in
+    Float64) or in an L2-resident global workspace (any n; the reference has no size limit, src/directLinearSolvers.jl:100)."""
+    dt = np.dtype(dtype)
+    rng = np.random.default_rng(n)
+    ns = 3
+    R = np.asfortranarray(rng.random((n - 1, ns)) / n).astype(dt)
+    B = np.asfortranarray(rng.standard_normal((n, ns))).astype(dt)
+    Rd = np.asfortranarray(rng.random((n, ns)) / n).astype(dt)
+    diag = (1.0 + rng.random(ns)).astype(dt)
+    dm = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).cuda().t()
+    X = tb.colmajor(n, ns, getattr(torch, dtype))
+    tb.levinson_(X, dm(R * diag), dm(B), torch.from_numpy(diag).cuda())
+    Y = tb.colmajor(n, ns, getattr(torch, dtype))
+    tb.durbin_(Y, dm(Rd))
+    xo = OC.c_levinson_batched(np.asfortranarray(R.astype(np.float64)), np.asfortranarray(B.astype(np.float64))) / diag.astype(np.float64)
+    yo = OC.c_durbin_batched(np.asfortranarray(Rd.astype(np.float64)))
+    # n recursion steps in the working precision against a Float64 oracle: rounding accumulates like a random walk,
+    # ~sqrt(n) * eps (matters for Float32 only: 4 * sqrt(12000) * eps32 = 5e-5; the reference in Float32 drifts the same way)
+    walk = 4.0 * np.sqrt(n) * PT.eps_of(dt)
+    PT.check("levinson n=%d %s (block kernel)" % (n, dtype), X.cpu().numpy(), xo, dt, extra=walk)
+    PT.check("durbin n=%d %s (block kernel)" % (n, dtype), Y.cpu().numpy(), yo, dt, extra=walk)

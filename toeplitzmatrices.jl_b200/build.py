@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libtoeplitz_b200.so")
-SOURCES = ["capi.cu", "comm.cu", "levinson.cu", "levinson_small.cu", "levinson_multiwarp.cu", "levinson_gen.cu", "rows_f64.cu", "rows_f32.cu", "cols_f64.cu", "cols_f32.cu", "cols_tma.cu"]
+SOURCES = ["capi.cu", "comm.cu", "levinson.cu", "levinson_small.cu", "levinson_multiwarp.cu", "levinson_gen.cu", "levinson_gen_mw.cu", "rows_f64.cu", "rows_f32.cu", "cols_f64.cu", "cols_f32.cu", "cols_tma.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

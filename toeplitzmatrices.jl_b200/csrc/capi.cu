@@ -566,8 +566,11 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     // ones (2 x 64 MiB of config 3, 256 MiB of config 5) stream through DRAM anyway and a partial window costs them
     // 15-30 % (profiles/experiments_r02.md)
     const size_t ws_in_flight = (size_t)nstr * (size_t)G * Np * sizeof(cx<R>);
-    const bool l2win = g_l2_persist_mb.load() > 0 && ws_in_flight <= ((size_t)g_l2_persist_mb.load() << 20);
-    if (!l2win) release_l2_carveout();      // a carve-out left behind by a smaller product halves the L2 everyone else sees
+    // ... and only for multi-group products (the overlapped pipeline the window was measured on): a single transform
+    // (factorize, a lone vector) would flip the device-wide limit back and forth between calls for nothing
+    const bool l2win = g_l2_persist_mb.load() > 0 && overlap && ws_in_flight <= ((size_t)g_l2_persist_mb.load() << 20);
+    if (!l2win && ws_in_flight > ((size_t)g_l2_persist_mb.load() << 20))
+        release_l2_carveout();              // a carve-out left behind by a smaller product halves the L2 this one sees
     for (int i = 0; i < nstr; ++i) {
         if (l2win) { apply_l2_window(stream_of[i], scratch_of[i], (size_t)G * Np * sizeof(cx<R>), nstr); w->win_set[i] = true; }
         else if (w->win_set[i]) { apply_l2_window(stream_of[i], nullptr, 0, 1); w->win_set[i] = false; }
@@ -708,7 +711,6 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
             TB_CUDA(launch_colsC<R>(h->log2l1, h->ta, pc, s), "k_colsC");
         }
     }
-    if (l2win && !overlap) { apply_l2_window(user_stream, nullptr, 0, 1); w->win_set[0] = false; }   // never leave a window on the caller's stream
     if (overlap) {
         for (int i = 0; i < nstr; ++i) {
             TB_CUDA(cudaEventRecord(w->ev_join[i], w->hs[i]), "join");

@@ -76,6 +76,100 @@ k_levinson_block(int64_t n64, int64_t nsys, const R* __restrict__ Rm, int64_t ld
     }
 }
 
+// Any n: one CTA per system, generator form (levinson_gen.cu) with the vectors in shared memory (GLOBAL = false) or in
+// a global-memory workspace that lives in L2 (GLOBAL = true, n beyond ~6000).  The shifting vector B costs nothing
+// here: B_k[s] = buf[n - k + s] in a buffer of 2n slots, so "shift up by one and insert alpha" is a moving base.
+// One barrier per step: the thread that owns slot k+1 publishes the next pivots (A[k+1], X[k+1]) in a two-slot
+// mailbox while it updates them.
+template <typename R, bool DURBIN, bool GLOBAL>
+__global__ void __launch_bounds__(512)
+k_levinson_gen_block(int64_t n64, int64_t nsys, const R* __restrict__ Rm, int64_t ldr, const R* __restrict__ Bm,
+                     int64_t ldb, R* __restrict__ Xm, int64_t ldx, const R* __restrict__ diag, R* __restrict__ work) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ R piv[2][2];
+    const int n = (int)n64;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int nr = DURBIN ? n : n - 1;
+    R* base = GLOBAL ? work + (size_t)blockIdx.x * (size_t)(4 * (size_t)n) : reinterpret_cast<R*>(smraw);
+    R* A = base;                    // n
+    R* Bb = A + n;                  // 2n
+    R* X = Bb + 2 * (size_t)n;      // n (levinson only)
+    for (int64_t sys = blockIdx.x; sys < nsys; sys += gridDim.x) {
+        const R dg = (!DURBIN && diag) ? diag[sys] : (R)1;
+        const bool scale = (dg != (R)1);
+        for (int i = tid; i < n; i += nth) {
+            R ri = 0, rim1 = (R)1;                     // r[i+1] and r[i] with r[0] = 1
+            if (i < nr) { ri = Rm[sys * ldr + i]; if (scale) ri /= dg; }
+            if (i >= 1) { rim1 = Rm[sys * ldr + i - 1]; if (scale) rim1 /= dg; }
+            A[i] = ri;
+            Bb[n + i] = rim1;
+            Bb[i] = 0;
+            if (!DURBIN) X[i] = -Bm[sys * ldb + i];
+        }
+        if (tid == 0) {
+            R r1 = 0;
+            if (nr > 0) { r1 = Rm[sys * ldr]; if (scale) r1 /= dg; }
+            piv[0][0] = r1;                            // A[0]
+            piv[0][1] = DURBIN ? (R)0 : -Bm[sys * ldb];
+        }
+        R alpha = 0, beta = 1;
+        __syncthreads();
+        for (int k = 0; k < n; ++k) {
+            beta *= ((R)1 - alpha * alpha);
+            const R ibeta = (R)1 / beta;
+            const R ak = piv[k & 1][0], xk = piv[k & 1][1];
+            const bool need_alpha = DURBIN || k < n - 1;
+            alpha = need_alpha ? -ak * ibeta : (R)0;
+            const R mu = -xk * ibeta;
+            R* B = Bb + (n - k);                       // B_k[s] = B[s]
+            for (int sidx = tid; sidx < n; sidx += nth) {
+                const R bo = B[sidx];
+                R xn = 0, an = 0;
+                if (!DURBIN) { xn = (sidx == k) ? mu : fma(mu, bo, X[sidx]); X[sidx] = xn; }
+                if (need_alpha) {
+                    const R ao = A[sidx];
+                    an = (sidx == k) ? alpha : fma(alpha, bo, ao);
+                    A[sidx] = an;
+                    B[sidx] = fma(alpha, ao, bo);
+                }
+                if (sidx == k + 1) { piv[(k + 1) & 1][0] = an; piv[(k + 1) & 1][1] = xn; }
+            }
+            if (need_alpha && tid == 0) Bb[n - k - 1] = alpha;     // head of B_{k+1}
+            __syncthreads();
+        }
+        for (int i = tid; i < n; i += nth) {
+            R v = DURBIN ? A[i] : X[i];
+            if (scale) v /= dg;
+            Xm[sys * ldx + i] = v;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename R, bool DURBIN>
+static int launch_levinson_gen_block(int64_t n, int64_t nsys, const R* r, int64_t ldr, const R* b, int64_t ldb, R* x, int64_t ldx,
+                                     const R* diag, cudaStream_t s) {
+    const size_t per_sys = (size_t)4 * n * sizeof(R);
+    if (per_sys <= 200 * 1024) {
+        auto kern = k_levinson_gen_block<R, DURBIN, false>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_sys);
+        if (e != cudaSuccess) return cuda_status(e, "levinson smem attribute");
+        const unsigned grid = (unsigned)(nsys < 148 * 4 ? nsys : 148 * 4);
+        kern<<<grid, 512, per_sys, s>>>(n, nsys, r, ldr, b, ldb, x, ldx, diag, nullptr);
+        count_launch();
+        return cuda_status(cudaGetLastError(), "levinson generator-form block kernel");
+    }
+    const unsigned grid = (unsigned)(nsys < 148 * 2 ? nsys : 148 * 2);
+    R* work = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&work), per_sys * grid, s);
+    if (e != cudaSuccess) return cuda_status(e, "levinson workspace");
+    k_levinson_gen_block<R, DURBIN, true><<<grid, 512, 0, s>>>(n, nsys, r, ldr, b, ldb, x, ldx, diag, work);
+    count_launch();
+    e = cudaGetLastError();
+    cudaFreeAsync(work, s);
+    return cuda_status(e, "levinson generator-form block kernel (global workspace)");
+}
+
 template <typename R, bool DURBIN>
 static int launch_levinson(int64_t n, int64_t nsys, const R* r, int64_t ldr, const R* b, int64_t ldb, R* x,
                            int64_t ldx, const R* diag, cudaStream_t s) {
@@ -107,12 +201,15 @@ static int launch_levinson(int64_t n, int64_t nsys, const R* r, int64_t ldr, con
         return cuda_status(cudaGetLastError(), "levinson warp kernel");
     }
     if (n <= 16 * LSPAN) {                    // 2 (n <= 1024) or 4 (n <= 2048) warps per system
-        const cudaError_t e = launch_levinson_mw<R, DURBIN>(n, nsys, r, ldr, b, ldb, x, ldx, diag, s);
+        const cudaError_t e = g_lev_gen ? launch_levinson_gen_mw<R, DURBIN>(n, nsys, r, ldr, b, ldb, x, ldx, diag, s)
+                                        : launch_levinson_mw<R, DURBIN>(n, nsys, r, ldr, b, ldb, x, ldx, diag, s);
         count_launch();
         return cuda_status(e, "levinson multi-warp kernel");
     }
+    if (n >= (1ll << 30)) return set_error(TB200_UNSUPPORTED, "levinson/durbin: n must be below 2^30");
     const size_t smem = (size_t)5 * n * sizeof(R);
-    if (smem > 200 * 1024) return set_error(TB200_UNSUPPORTED, "levinson/durbin: n too large for the shared-memory kernel");
+    if (g_lev_gen || smem > 200 * 1024)        // any n: generator form, shared memory or an L2-resident global workspace
+        return launch_levinson_gen_block<R, DURBIN>(n, nsys, r, ldr, b, ldb, x, ldx, diag, s);
     auto kern = k_levinson_block<R, DURBIN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e, "levinson smem attribute");

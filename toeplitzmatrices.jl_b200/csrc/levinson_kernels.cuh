@@ -235,6 +235,10 @@ cudaError_t launch_levinson_mw(int64_t n, int64_t nsys, const R* r, int64_t ldr,
 template <typename R, bool DURBIN>
 cudaError_t launch_levinson_gen(int64_t n, int64_t nsys, const R* r, int64_t ldr, const R* b, int64_t ldb, R* x, int64_t ldx,
                                 const R* diag, cudaStream_t s);
+// generator form, 2 or 4 warps per system, 512 < n <= 2048 (levinson_gen_mw.cu)
+template <typename R, bool DURBIN>
+cudaError_t launch_levinson_gen_mw(int64_t n, int64_t nsys, const R* r, int64_t ldr, const R* b, int64_t ldb, R* x, int64_t ldx,
+                                   const R* diag, cudaStream_t s);
 extern int g_lev_gen;     // 1 (default): n <= 512 takes the generator-form kernels; 0: the dot-product kernels (tb200_set_option("lev_gen"))
 
 }  // namespace tb
