@@ -33,6 +33,7 @@ static std::atomic<long long> g_host_chunk_bytes{256ll << 20};
 static std::atomic<long long> g_krylov_work_bytes{16ll << 30};   // work-vector budget of the batched cgs / cg (columns per chunk)
 static std::atomic<int> g_time_passes{0};
 static std::atomic<int> g_ca_fuse{0};            // 1: pass C of a group + pass A of the next one on its stream as one launch; 2: + async x tile
+static std::atomic<int> g_pdl{1};                // programmatic dependent launch of passes B / C: 0 off, 1 products without group overlap, 2 always
 static std::atomic<int> g_l2_persist_mb{64};     // persisting-L2 carve-out for the two-level workspaces (0 = off); +4 % on config 2
 static std::atomic<int> g_tma{0};                // TMA-staged strided passes (tma_cols.cuh) where eligible; measured, see DESIGN.md
 extern int g_lev_gen;                            // levinson.cu
@@ -649,6 +650,9 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     const bool fuse = false;        // experiment build only (csrc/experiments/ca_kernels.cuh): measured slower
     (void)halfA; (void)halfC;
 #endif
+    // PDL hides the launch latency between the passes of one product; the per-pass timers bracket launches with events,
+    // which would serialise them again, so the two are exclusive
+    const bool use_pdl = !g_time_passes.load() && !tmaA && !tmaC && (g_pdl.load() >= 2 || (g_pdl.load() == 1 && !overlap));
     long long group_index = 0;
     for (long long f0 = 0; f0 < c.nfft; f0 += G, ++group_index) {
         const long long g = std::min(G, c.nfft - f0);
@@ -695,13 +699,15 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
                 pb.y = c.y; pb.y_mode = IO_SPEC; pb.spec = nullptr;
                 if (g != 1 || c.nfft != 1) return set_error(TB200_BAD_ARG, "internal: forward-only runs one transform");
             }
+            pb.pdl = (use_pdl && c.do_fwd) ? 1 : 0;          // behind pass A of this group
             count_launch();
             PassTimer pt(1, s);
             TB_CUDA(launch_rows<R>(h->log2l2, pb, num_sms(), s), "k_rows (pass B)");
         }
         // pass C (deferred into the next group's fused launch when this stream has one)
         if (c.do_inv && !(fuse && f0 + (long long)nstr * G < c.nfft)) {
-            const ConvArgs<R> pc = args_C(f0, g, scratch);
+            ConvArgs<R> pc = args_C(f0, g, scratch);
+            pc.pdl = use_pdl ? 1 : 0;                          // behind pass B of this group
             count_launch();
             PassTimer pt(2, s);
             if (tmaC) {
@@ -921,6 +927,7 @@ int tb200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "host_chunk_bytes")) { g_host_chunk_bytes = std::max<int64_t>(value, 1 << 20); return TB200_OK; }
     if (!strcmp(name, "time_passes")) { g_time_passes = value ? 1 : 0; return TB200_OK; }
     if (!strcmp(name, "ca_fuse")) { g_ca_fuse = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 2); return TB200_OK; }
+    if (!strcmp(name, "pdl")) { g_pdl = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 2); return TB200_OK; }
     if (!strcmp(name, "l2_persist_mb")) { g_l2_persist_mb = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 1024); return TB200_OK; }
     if (!strcmp(name, "lev_gen")) { g_lev_gen = (int)(value & 1); return TB200_OK; }
     if (!strcmp(name, "prune_half")) { g_prune_half = value ? 1 : 0; return TB200_OK; }

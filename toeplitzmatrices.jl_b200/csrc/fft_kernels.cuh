@@ -45,7 +45,14 @@ struct ConvArgs {
     // per-column device scalars (batched Krylov: r -= alpha_j * A * uh fused into the epilogue): the effective alpha of
     // user column j is alpha * (col_alpha[j*stride], col_alpha[j*stride + 1]); NULL = none
     const double* col_alpha; int col_alpha_stride;
+    // host side only: launch this pass with programmatic stream serialization (its CTAs may become resident while the
+    // previous pass of the same product drains; they block in griddepcontrol.wait until that pass has completed)
+    int pdl;
 };
+
+// Programmatic dependent launch (PDL).  Both are no-ops in a kernel that was launched normally.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Inter-level twiddles of one thread (fixed column j2): w^(k1(i) j2) = w^(kbase(t) j2) * w^(delta_i j2).
 // One split-table lookup for the base, LOGE coalesced loads from the [E][N2] table, E-1 complex multiplies.
@@ -162,6 +169,8 @@ k_rows(const ConvArgs<R> p) {
     const int slot = threadIdx.x / NT, t = threadIdx.x % NT;
     cx<R>* sm = reinterpret_cast<cx<R>*>(smraw) + slot * L;
     RowMap<R> map;
+    pdl_wait();                    // pass B of a PDL chain: the workspace is complete from here on
+    pdl_launch_dependents();
 
     for (long long f0 = (long long)blockIdx.x * TS; f0 < p.nfft; f0 += (long long)gridDim.x * TS) {
         const long long f = f0 + slot;
@@ -239,6 +248,7 @@ k_colsA(const ConvArgs<R> p) {
     const long long f = blockIdx.x / tiles;
     const int j2 = (int)(blockIdx.x % tiles) * TA + q;
     ColMap<TA> map{q};
+    pdl_launch_dependents();
     cx<R> a[E];
     {
         const InView<R> in(p, f);
@@ -272,7 +282,8 @@ k_colsC(const ConvArgs<R> p) {
     cx<R> a[E];
     {
         cx<R> w[E];
-        level_twiddles<R, F>(p, t, j2, w);
+        level_twiddles<R, F>(p, t, j2, w);      // tables only: may run before the previous pass has finished
+        pdl_wait();
 #pragma unroll
         for (int i = 0; i < E; ++i) a[i] = cmulc(ld_stream(in + ((long long)F::pos_of_reg(i, t) << l2)), w[i]);
     }

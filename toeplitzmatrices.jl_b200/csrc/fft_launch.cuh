@@ -1,6 +1,7 @@
 // Host-side launchers for the templated FFT kernels (one translation unit per
 // precision x kernel family so nvcc can build them in parallel).
 #pragma once
+#include <string.h>
 #include "fft_kernels.cuh"
 
 namespace tb {
@@ -16,6 +17,27 @@ template <typename R> cudaError_t launch_colsC(int log2l1, int ta, const ConvArg
 // fused pass C (pc) + pass A of the next group on the same workspace (pa); experiments/cols_ca.cu, TB_EXP_CA builds only
 template <typename R> cudaError_t launch_colsCA(int log2l1, int ta, const ConvArgs<R>& pc, const ConvArgs<R>& pa, bool half, bool stage, cudaStream_t s);
 template <typename R> bool cols_ca_supported(int log2l1, int ta);
+
+// One pass: a plain launch, or -- a.pdl -- a programmatic dependent launch behind the previous pass of the same product
+template <typename R, typename K>
+cudaError_t launch_pass(K kern, unsigned grid, int threads, size_t smem, cudaStream_t s, const ConvArgs<R>& a) {
+    if (!a.pdl) {
+        kern<<<grid, threads, smem, s>>>(a);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
 
 template <typename R, int LOG2L>
 cudaError_t launch_rows_one(const ConvArgs<R>& a, int num_sms, cudaStream_t s) {
@@ -35,8 +57,7 @@ cudaError_t launch_rows_one(const ConvArgs<R>& a, int num_sms, cudaStream_t s) {
     long long cap = (long long)num_sms * 16;
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;
-    kern<<<(unsigned)ctas, threads, smem, s>>>(a);
-    return cudaGetLastError();
+    return launch_pass(kern, (unsigned)ctas, threads, smem, s, a);
 }
 
 // pruned variants (half of the embedding is padding) exist for radix-16 threads with at least one full stage
@@ -68,8 +89,7 @@ cudaError_t launch_cols_v(const ConvArgs<R>& a, cudaStream_t s) {
     }
     const long long tiles = (1LL << a.log2n2) / TA;
     const long long grid = tiles * a.nfft;
-    kern<<<(unsigned)grid, threads, smem, s>>>(a);
-    return cudaGetLastError();
+    return launch_pass(kern, (unsigned)grid, threads, smem, s, a);
 }
 
 // ---- TMA-staged strided passes (tma_cols.cuh), instantiated for the plans of the BASELINE configs ----------------
