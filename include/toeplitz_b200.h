@@ -202,6 +202,17 @@ int tb200_comm_size(tb200_comm_t c, int* nranks, int* nlocal);
 int tb200_bcast_spectrum(tb200_comm_t c, tb200_handle_t* handles, int nhandles, int root, void** streams);
 int tb200_comm_destroy(tb200_comm_t c);
 
+/* Container algebra on the stored coefficient vectors (the reference's generic broadcasts on A.vc / A.vr / A.v:
+ * src/toeplitz.jl:66-140 tril, triu, +, -, scalar product, conj, copyto!, fill!, lmul!, rmul!, src/special.jl:13-33,77-84,223-248,
+ * src/hankel.jl:75-130 incl. reverse).  op: 0 out = alpha*a + beta*b (b may be NULL), 1 conj(a), 2 real(a), 3 imag(a),
+ * 4 fill(alpha).  Every operand has its own TB200_* dtype (promotion happens in the kernel); rev_a / rev_b read the
+ * operand back to front.  Asynchronous on `stream`.                                                                */
+int tb200_vec_op(int op, int64_t n, const void* a, int dtype_a, int rev_a, const void* b, int dtype_b, int rev_b, void* out,
+                 int dtype_out, const double alpha[2], const double beta[2], void* stream);
+/* `==` on two stored vectors (src/toeplitz.jl:114-121, src/hankel.jl:96): *equal = 1 iff all n entries agree.
+ * b == NULL compares against zero (iszero / isdiag).  Synchronises `stream` (returns a host scalar).               */
+int tb200_vec_equal(int64_t n, const void* a, int dtype_a, const void* b, int dtype_b, int* equal, void* stream);
+
 /* tuning / introspection: number of kernel launches issued by this library so far      */
 int64_t tb200_launch_count(void);
 int tb200_set_option(const char* name, int64_t value);

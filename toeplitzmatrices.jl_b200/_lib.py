@@ -24,7 +24,7 @@ EXPORTS = [
     "tb200_pass_times", "tb200_pass_times_ex", "tb200_trench", "tb200_tri_smallinv", "tb200_levinson_multirhs",
     "tb200_cgs_batched", "tb200_cg_batched", "tb200_spectrum_ready",
     "tb200_comm_init", "tb200_comm_unique_id", "tb200_comm_init_rank", "tb200_comm_size", "tb200_bcast_spectrum",
-    "tb200_comm_destroy",
+    "tb200_comm_destroy", "tb200_vec_op", "tb200_vec_equal",
 ]
 
 
@@ -92,6 +92,8 @@ def lib() -> ctypes.CDLL:
         "tb200_set_option": [ctypes.c_char_p, i64],
         "tb200_pass_times": [pd, pi64],
         "tb200_pass_times_ex": [pd, pi64, ctypes.c_int],
+        "tb200_vec_op": [ci, i64, vp, ci, ci, vp, ci, ci, vp, ci, pd, pd, vp],
+        "tb200_vec_equal": [i64, vp, ci, vp, ci, pi, vp],
         "tb200_trench": [ci, i64, vp, vp, i64, dbl, vp],
         "tb200_tri_smallinv": [ci, i64, vp, vp, vp],
         "tb200_levinson_multirhs": [ci, i64, i64, vp, vp, i64, vp, i64, vp],

@@ -291,4 +291,61 @@ __global__ void k_direct_mul(void* y, long long ldy, int y_cplx, const void* x, 
     else reinterpret_cast<R*>(y)[col * ldy + i] = acc.x;
 }
 
+// Container algebra on the stored coefficient vectors (src/toeplitz.jl:66-140, src/special.jl:13-33,77-84,
+// 223-248, src/hankel.jl:75-130): one elementwise kernel for every dtype combination.  Values travel as complex double
+// (exact for every supported input type); dtype codes are the TB200_* ones (0 f32, 1 f64, 2 c32, 3 c64).
+enum VecOp : int { VOP_AXPBY = 0, VOP_CONJ = 1, VOP_REAL = 2, VOP_IMAG = 3, VOP_FILL = 4 };
+
+__device__ __forceinline__ double2 vec_load(const void* p, int dt, long long i) {
+    switch (dt) {
+    case 0: return make_double2((double)reinterpret_cast<const float*>(p)[i], 0.0);
+    case 1: return make_double2(reinterpret_cast<const double*>(p)[i], 0.0);
+    case 2: { const float2 v = reinterpret_cast<const float2*>(p)[i]; return make_double2((double)v.x, (double)v.y); }
+    default: return reinterpret_cast<const double2*>(p)[i];
+    }
+}
+__device__ __forceinline__ void vec_store(void* p, int dt, long long i, double2 v) {
+    switch (dt) {
+    case 0: reinterpret_cast<float*>(p)[i] = (float)v.x; break;
+    case 1: reinterpret_cast<double*>(p)[i] = v.x; break;
+    case 2: reinterpret_cast<float2*>(p)[i] = make_float2((float)v.x, (float)v.y); break;
+    default: reinterpret_cast<double2*>(p)[i] = v; break;
+    }
+}
+// out[i] = op(a[ia], b[ib]); rev_a / rev_b read the operand back to front (reverse(v), src/hankel.jl:112-121)
+__global__ void k_vec_op(int op, long long n, const void* a, int da, int rev_a, const void* b, int db, int rev_b, void* out,
+                         int dout, double2 alpha, double2 beta) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double2 r = make_double2(0.0, 0.0);
+        const double2 va = a ? vec_load(a, da, rev_a ? n - 1 - i : i) : r;
+        switch (op) {
+        case VOP_AXPBY: {
+            r.x = alpha.x * va.x - alpha.y * va.y;
+            r.y = alpha.x * va.y + alpha.y * va.x;
+            if (b) {
+                const double2 vb = vec_load(b, db, rev_b ? n - 1 - i : i);
+                r.x += beta.x * vb.x - beta.y * vb.y;
+                r.y += beta.x * vb.y + beta.y * vb.x;
+            }
+            break;
+        }
+        case VOP_CONJ: r = make_double2(va.x, -va.y); break;
+        case VOP_REAL: r = make_double2(va.x, 0.0); break;
+        case VOP_IMAG: r = make_double2(va.y, 0.0); break;
+        default: r = alpha; break;            // VOP_FILL
+        }
+        vec_store(out, dout, i, r);
+    }
+}
+// number of positions where a != b (==, isequal on the stored vectors); result accumulated into *count
+__global__ void k_vec_mismatch(long long n, const void* a, int da, const void* b, int db, unsigned long long* count) {
+    unsigned long long c = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double2 va = vec_load(a, da, i), vb = b ? vec_load(b, db, i) : make_double2(0.0, 0.0);     // b == NULL: iszero
+        c += (va.x != vb.x || va.y != vb.y) ? 1ull : 0ull;
+    }
+    for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
 }  // namespace tb

@@ -1341,6 +1341,40 @@ int tb200_levinson_multirhs(int dtype, int64_t n, int64_t nrhs, const void* vc, 
     return TB200_OK;
 }
 
+int tb200_vec_op(int op, int64_t n, const void* a, int dtype_a, int rev_a, const void* b, int dtype_b, int rev_b, void* out,
+                 int dtype_out, const double alpha[2], const double beta[2], void* stream) {
+    if (op < 0 || op > VOP_FILL) return set_error(TB200_BAD_ARG, "unknown vector op %d", op);
+    if (n < 0) return set_error(TB200_BAD_ARG, "bad length");
+    if (n == 0) return TB200_OK;
+    if (!out || (!a && op != VOP_FILL)) return set_error(TB200_BAD_ARG, "NULL argument");
+    if (!dt_valid(dtype_out) || (a && !dt_valid(dtype_a)) || (b && !dt_valid(dtype_b))) return set_error(TB200_BAD_ARG, "unknown dtype");
+    const double2 al = make_double2(alpha ? alpha[0] : 1.0, alpha ? alpha[1] : 0.0);
+    const double2 be = make_double2(beta ? beta[0] : 0.0, beta ? beta[1] : 0.0);
+    k_vec_op<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(op, n, a, dtype_a, rev_a, b, dtype_b, rev_b, out, dtype_out, al, be);
+    count_launch();
+    return cuda_status(cudaGetLastError(), "k_vec_op");
+}
+
+int tb200_vec_equal(int64_t n, const void* a, int dtype_a, const void* b, int dtype_b, int* equal, void* stream) {
+    if (!equal) return set_error(TB200_BAD_ARG, "NULL argument");
+    *equal = 1;
+    if (n <= 0) return TB200_OK;
+    if (!a || !dt_valid(dtype_a) || (b && !dt_valid(dtype_b))) return set_error(TB200_BAD_ARG, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    std::shared_ptr<DevBuf> cnt;
+    TB_TRY(dev_alloc_on(cnt, sizeof(unsigned long long), "mismatch counter", s));
+    TB_CUDA(cudaMemsetAsync(cnt->p, 0, sizeof(unsigned long long), s), "memset");
+    k_vec_mismatch<<<ew_grid(n), 256, 0, s>>>(n, a, dtype_a, b, dtype_b, (unsigned long long*)cnt->p);
+    count_launch();
+    TB_CUDA(cudaGetLastError(), "k_vec_mismatch");
+    unsigned long long hcnt = 0;
+    TB_CUDA(cudaMemcpyAsync(&hcnt, cnt->p, sizeof(hcnt), cudaMemcpyDeviceToHost, s), "mismatch count");
+    TB_CUDA(cudaStreamSynchronize(s), "mismatch sync");
+    TB_TRY(retire_after(s));
+    *equal = hcnt == 0 ? 1 : 0;
+    return TB200_OK;
+}
+
 int tb200_tri_smallinv(int dtype, int64_t n, const void* v, void* out, void* stream) {
     if (!dt_valid(dtype)) return set_error(TB200_BAD_ARG, "unknown dtype");
     if (n < 1 || n > 64) return set_error(TB200_BAD_ARG, "smallinv is the n <= 64 base case, got n = %lld", (long long)n);
