@@ -43,6 +43,30 @@ __device__ __forceinline__ void dot_acc(double2 a, double2 b, double& re, double
     im = fma(a.x, b.y, fma(-a.y, b.x, im));
 }
 
+// Sum of `count` partial records of four doubles by one CTA of 256 threads, in a fixed order (thread t takes records
+// t, t + 256, ...; then lanes, then warps): bit-for-bit reproducible, and ~100x less latency than one thread walking
+// the records through L2.  `red` is the caller's [4][8] shared scratch; the result is valid in thread 0.
+__device__ __forceinline__ double4 final_sum4(const double* __restrict__ partials, unsigned count, double (*red)[8]) {
+    double v[4] = {0, 0, 0, 0};
+    for (unsigned b = threadIdx.x; b < count; b += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] += __ldcg(&partials[(size_t)b * 4 + k]);
+    }
+    __syncthreads();                       // the caller's earlier use of `red` is over
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v[k];
+    }
+    __syncthreads();
+    double4 s = make_double4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < 8; ++w) { s.x += red[0][w]; s.y += red[1][w]; s.z += red[2][w]; s.w += red[3][w]; }
+    }
+    return s;
+}
+
 // out[0..1] = dot(a1, b1), out[2..3] = dot(a2, b2) (second pair optional).  Deterministic:
 // per-CTA partials, the last CTA to finish sums them in index order.
 template <typename T>
@@ -74,11 +98,9 @@ k_dot2(const T* __restrict__ a1, const T* __restrict__ b1, const T* __restrict__
         is_last = (done == gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last && threadIdx.x < 4) {
-        double s = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * 4 + threadIdx.x]);
-        out[threadIdx.x] = s;
-        if (threadIdx.x == 0) *counter = 0;
+    if (is_last) {
+        const double4 s = final_sum4(partials, gridDim.x, red);
+        if (threadIdx.x == 0) { out[0] = s.x; out[1] = s.y; out[2] = s.z; out[3] = s.w; *counter = 0; }
     }
 }
 

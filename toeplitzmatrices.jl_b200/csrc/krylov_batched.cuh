@@ -63,11 +63,14 @@ k_bdot2(const T* __restrict__ a1, const T* __restrict__ b1, long long ld1, const
         is_last = (done == gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last && threadIdx.x < 4) {
-        double s = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&mine[(size_t)b * 4 + threadIdx.x]);
-        st[j].dot[threadIdx.x] = s;
-        if (threadIdx.x == 0) counters[j] = 0;
+    if (is_last) {
+        // the last CTA of the column sums the per-CTA partials in a fixed order (deterministic), all 256 threads at it:
+        // one thread walking 2368 partials through L2 took longer than the sweep itself at n = 2^24
+        const double4 s = final_sum4(mine, gridDim.x, red);
+        if (threadIdx.x == 0) {
+            st[j].dot[0] = s.x; st[j].dot[1] = s.y; st[j].dot[2] = s.z; st[j].dot[3] = s.w;
+            counters[j] = 0;
+        }
     }
 }
 
