@@ -100,8 +100,14 @@ __device__ __forceinline__ void gen_superrows(GenState<R, S, DURBIN>& st, int n,
 
 // CTAs of 4 warps per SM the register budget is cut for: the state is (2 or 3) * 4S values per lane plus ~35 registers
 // of addressing / scalars; the budgets below are the largest occupancy that compiles without spills
+#ifndef TB_GEN_LEV_CTAS
+#define TB_GEN_LEV_CTAS 4
+#endif
+#ifndef TB_GEN_DUR_CTAS
+#define TB_GEN_DUR_CTAS 4
+#endif
 template <typename R, bool DURBIN, int S> constexpr int gen_min_ctas() {
-    if (sizeof(R) == 8) return DURBIN ? (S == 4 ? 4 : 5) : (S >= 3 ? 3 : 4);
+    if (sizeof(R) == 8) return DURBIN ? (S == 4 ? TB_GEN_DUR_CTAS : 5) : (S >= 3 ? TB_GEN_LEV_CTAS : 4);
     return DURBIN ? (S == 4 ? 5 : 6) : (S == 4 ? 4 : 6);
 }
 
