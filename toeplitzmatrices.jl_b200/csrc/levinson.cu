@@ -389,6 +389,183 @@ k_levinson_rhs(int n, int64_t nrhs, const R* __restrict__ rnorm, const R* __rest
         }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same shape in generator form (levinson_gen.cu): the shared part is the Durbin recursion on (A, B); row k of
+// the table holds the WHOLE shifting vector B_k (reverse(y_k) in slots < k, the generator v_k in slots >= k) and
+// 1/beta_k.  A right-hand side then needs no dot product at all:  mu = -X[k]/beta_k ;  X += mu*B_k ;  X[k] = mu
+// with X = x_k in slots < k and -(b - T x_k) in slots >= k -- n FMAs per step and column, one pivot broadcast, no
+// reduction; NC columns share every table row a warp loads.
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, int S, int SC, int J>
+__device__ __forceinline__ void btab_step(R* a, R* b, R& alpha, R& beta, int k, int n, int lane, int lb, R* __restrict__ btab,
+                                          R* __restrict__ ibeta_tab) {
+    constexpr int N = S * LB;
+    constexpr int PH = J;
+    beta *= ((R)1 - alpha * alpha);
+    const R ibeta = fast_rcp2(beta);
+    if (lane == 0) ibeta_tab[k] = ibeta;
+    R* row = btab + (long long)k * (S * LSPAN);
+#pragma unroll
+    for (int i = 0; i < N; ++i) row[(i / LB) * LSPAN + lane * LB + (i % LB)] = b[phys(i, PH)];
+    if (k < n - 1) {
+        const R ak = __shfl_sync(0xffffffffu, a[SC * LB + J], lb);
+        alpha = -ak * ibeta;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const R ao = a[i], bo = b[phys(i, PH)];
+            a[i] = fma(alpha, bo, ao);
+            b[phys(i, PH)] = fma(alpha, ao, bo);
+        }
+        if (lane == lb) a[SC * LB + J] = alpha;
+        shift_up<R, S, PH>(b, alpha, lane);
+    }
+}
+template <typename R, int S, int SC>
+__device__ __forceinline__ void btab_superrows(R* a, R* b, R& alpha, R& beta, int n, int lane, R* btab, R* ibeta_tab) {
+    if constexpr (SC < S) {
+        for (int lb = 0; lb < 32; ++lb) {
+            const int k0 = SC * LSPAN + lb * LB;
+            if (k0 >= n) break;
+            if (k0 + 0 < n) btab_step<R, S, SC, 0>(a, b, alpha, beta, k0 + 0, n, lane, lb, btab, ibeta_tab);
+            if (k0 + 1 < n) btab_step<R, S, SC, 1>(a, b, alpha, beta, k0 + 1, n, lane, lb, btab, ibeta_tab);
+            if (k0 + 2 < n) btab_step<R, S, SC, 2>(a, b, alpha, beta, k0 + 2, n, lane, lb, btab, ibeta_tab);
+            if (k0 + 3 < n) btab_step<R, S, SC, 3>(a, b, alpha, beta, k0 + 3, n, lane, lb, btab, ibeta_tab);
+        }
+        btab_superrows<R, S, SC + 1>(a, b, alpha, beta, n, lane, btab, ibeta_tab);
+    }
+}
+// one warp: the shared recursion of T = SymToeplitz(vc) (n x n), rows B_k and 1/beta_k for k = 0 .. n-1
+template <typename R, int S>
+__global__ void __launch_bounds__(32)
+k_levinson_btab(int n, const R* __restrict__ vc, R* __restrict__ btab, R* __restrict__ ibeta_tab) {
+    __shared__ R r_s[S * LSPAN + LB];
+    const int lane = threadIdx.x;
+    const R d = vc[0];
+    if (lane == 0) r_s[0] = (R)1;
+    for (int i = lane; i < S * LSPAN; i += 32) r_s[1 + i] = (i < n - 1) ? ((d != (R)1) ? vc[i + 1] / d : vc[i + 1]) : (R)0;
+    __syncwarp();
+    R a[S * LB], b[S * LB];
+#pragma unroll
+    for (int sr = 0; sr < S; ++sr)
+#pragma unroll
+        for (int j = 0; j < LB; ++j) {
+            const int sl = sr * LSPAN + lane * LB + j;
+            a[sr * LB + j] = r_s[1 + sl];
+            b[sr * LB + j] = (sl < n) ? r_s[sl] : (R)0;
+        }
+    R alpha = 0, beta = 1;
+    btab_superrows<R, S, 0>(a, b, alpha, beta, n, lane, btab, ibeta_tab);
+}
+
+template <typename R, int S, int NC, int SC, int J>
+__device__ __forceinline__ void rhsg_step(R (*x)[S * LB], int k, int lane, int lb, const R* __restrict__ btab,
+                                          const R* __restrict__ ibeta_tab) {
+    constexpr int N = S * LB;
+    const R* row = btab + (long long)k * (S * LSPAN) + lane * LB;
+    R bk[N];
+#pragma unroll
+    for (int sr = 0; sr < S; ++sr) {
+        if constexpr (sizeof(R) == 8) {
+            const double2 v0 = __ldg(reinterpret_cast<const double2*>(row + sr * LSPAN));
+            const double2 v1 = __ldg(reinterpret_cast<const double2*>(row + sr * LSPAN) + 1);
+            bk[sr * LB + 0] = v0.x; bk[sr * LB + 1] = v0.y; bk[sr * LB + 2] = v1.x; bk[sr * LB + 3] = v1.y;
+        } else {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(row + sr * LSPAN));
+            bk[sr * LB + 0] = v.x; bk[sr * LB + 1] = v.y; bk[sr * LB + 2] = v.z; bk[sr * LB + 3] = v.w;
+        }
+    }
+    const R ibeta = __ldg(ibeta_tab + k);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const R xk = __shfl_sync(0xffffffffu, x[c][SC * LB + J], lb);
+        const R mu = -xk * ibeta;
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[c][i] = fma(mu, bk[i], x[c][i]);
+        if (lane == lb) x[c][SC * LB + J] = mu;
+    }
+}
+template <typename R, int S, int NC, int SC>
+__device__ __forceinline__ void rhsg_superrows(R (*x)[S * LB], int n, int lane, const R* btab, const R* ibeta_tab) {
+    if constexpr (SC < S) {
+        for (int lb = 0; lb < 32; ++lb) {
+            const int k0 = SC * LSPAN + lb * LB;
+            if (k0 >= n) break;
+            if (k0 + LB <= n) {
+                rhsg_step<R, S, NC, SC, 0>(x, k0 + 0, lane, lb, btab, ibeta_tab);
+                rhsg_step<R, S, NC, SC, 1>(x, k0 + 1, lane, lb, btab, ibeta_tab);
+                rhsg_step<R, S, NC, SC, 2>(x, k0 + 2, lane, lb, btab, ibeta_tab);
+                rhsg_step<R, S, NC, SC, 3>(x, k0 + 3, lane, lb, btab, ibeta_tab);
+                continue;
+            }
+            if (k0 + 0 < n) rhsg_step<R, S, NC, SC, 0>(x, k0 + 0, lane, lb, btab, ibeta_tab);
+            if (k0 + 1 < n) rhsg_step<R, S, NC, SC, 1>(x, k0 + 1, lane, lb, btab, ibeta_tab);
+            if (k0 + 2 < n) rhsg_step<R, S, NC, SC, 2>(x, k0 + 2, lane, lb, btab, ibeta_tab);
+            if (k0 + 3 < n) rhsg_step<R, S, NC, SC, 3>(x, k0 + 3, lane, lb, btab, ibeta_tab);
+        }
+        rhsg_superrows<R, S, NC, SC + 1>(x, n, lane, btab, ibeta_tab);
+    }
+}
+// one warp per NC right-hand-side columns; X = T \ B; diag = vc[0]
+template <typename R, int S, int NC>
+__global__ void __launch_bounds__(128, (sizeof(R) == 8 && NC * S > 8) ? 2 : 3)
+k_levinson_rhs_gen(int n, int64_t nrhs, const R* __restrict__ vc, const R* __restrict__ Bm, int64_t ldb, R* __restrict__ Xm, int64_t ldx,
+                   const R* __restrict__ btab, const R* __restrict__ ibeta_tab) {
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const int64_t col0 = NC * ((int64_t)blockIdx.x * (blockDim.x >> 5) + wic);
+    if (col0 >= nrhs) return;
+    R x[NC][S * LB];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int64_t col = (col0 + c < nrhs) ? col0 + c : nrhs - 1;        // surplus columns shadow the last one, never stored
+        const R* bc = Bm + col * ldb;
+#pragma unroll
+        for (int sr = 0; sr < S; ++sr)
+#pragma unroll
+            for (int j = 0; j < LB; ++j) {
+                const int sl = sr * LSPAN + lane * LB + j;
+                x[c][sr * LB + j] = (sl < n) ? -bc[sl] : (R)0;
+            }
+    }
+    rhsg_superrows<R, S, NC, 0>(x, n, lane, btab, ibeta_tab);
+    const R d = vc[0];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        if (col0 + c >= nrhs) break;
+        R* out = Xm + (col0 + c) * ldx;
+#pragma unroll
+        for (int sr = 0; sr < S; ++sr)
+#pragma unroll
+            for (int j = 0; j < LB; ++j) {
+                const int i = sr * LSPAN + lane * LB + j;
+                if (i < n) out[i] = (d != (R)1) ? x[c][sr * LB + j] / d : x[c][sr * LB + j];
+            }
+    }
+}
+
+template <typename R>
+static int launch_levinson_multirhs_gen(int64_t n, int64_t nrhs, const R* vc, const R* B, int64_t ldb, R* X, int64_t ldx,
+                                        R* work /* n*S*128 + n */, cudaStream_t s) {
+    const int S = (int)((n + LSPAN - 1) / LSPAN);
+    R* btab = work;                                   // first: keeps the table rows 16-byte aligned
+    R* ibeta_tab = btab + n * (int64_t)(S * LSPAN);
+#ifndef TB_MRHS_NC
+#define TB_MRHS_NC 4
+#endif
+    constexpr int NC = TB_MRHS_NC;                    // right-hand sides per warp (they share every table row the warp loads)
+    const int wpc = 4;
+    const int64_t ngroups = (nrhs + NC - 1) / NC;
+    const unsigned grid = (unsigned)((ngroups + wpc - 1) / wpc);
+#define TB_MRG_CASE(SV)                                                                                               \
+    case SV:                                                                                                          \
+        k_levinson_btab<R, SV><<<1, 32, 0, s>>>((int)n, vc, btab, ibeta_tab);                                        \
+        k_levinson_rhs_gen<R, SV, NC><<<grid, wpc * 32, 0, s>>>((int)n, nrhs, vc, B, ldb, X, ldx, btab, ibeta_tab);  \
+        break;
+    switch (S) { TB_MRG_CASE(1) TB_MRG_CASE(2) TB_MRG_CASE(3) TB_MRG_CASE(4) }
+#undef TB_MRG_CASE
+    count_launch(2);
+    return cuda_status(cudaGetLastError(), "multi-RHS levinson kernels (generator form)");
+}
+
 template <typename R>
 static int launch_levinson_multirhs(int64_t n, int64_t nrhs, const R* vc, const R* B, int64_t ldb, R* X, int64_t ldx,
                                     R* work /* n*S*128 + n + n */, cudaStream_t s) {
@@ -414,6 +591,10 @@ static int launch_levinson_multirhs(int64_t n, int64_t nrhs, const R* vc, const 
 int levinson_multirhs_dispatch(int dtype, int64_t n, int64_t nrhs, const void* vc, const void* B, int64_t ldb, void* X,
                                int64_t ldx, void* work, cudaStream_t s) {
     if (n < 2 || n > 4 * LSPAN) return set_error(TB200_UNSUPPORTED, "multi-RHS levinson: 2 <= n <= 512 (use tb200_levinson_batched)");
+    if (g_lev_gen) {
+        if (dtype == TB200_F64) return launch_levinson_multirhs_gen<double>(n, nrhs, (const double*)vc, (const double*)B, ldb, (double*)X, ldx, (double*)work, s);
+        if (dtype == TB200_F32) return launch_levinson_multirhs_gen<float>(n, nrhs, (const float*)vc, (const float*)B, ldb, (float*)X, ldx, (float*)work, s);
+    }
     if (dtype == TB200_F64) return launch_levinson_multirhs<double>(n, nrhs, (const double*)vc, (const double*)B, ldb, (double*)X, ldx, (double*)work, s);
     if (dtype == TB200_F32) return launch_levinson_multirhs<float>(n, nrhs, (const float*)vc, (const float*)B, ldb, (float*)X, ldx, (float*)work, s);
     return set_error(TB200_UNSUPPORTED, "levinson: only real Float32/Float64 systems");
