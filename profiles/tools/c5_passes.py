@@ -1,16 +1,15 @@
+"""Per-pass times of config 5a (Hankel{ComplexF32} n = 2^24) under plan options (column tile width, level split)."""
 import sys, os
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch, toeplitz_b200 as tb
 n = 1 << 24
 v = torch.randn(2 * n - 1, dtype=torch.complex64, device="cuda")
 x = torch.randn(n, dtype=torch.complex64, device="cuda")
 y = torch.empty_like(x)
-F = tb.factorize(tb.Hankel(v, (n, n)))
-for opt in ({}, {"force_l1": 12}, {"force_l1": 12, "pipe_b": 1}, {"force_l1": 12, "pipe_b": 1, "ta_cap": 4}):
+for opt in ({}, {"ta_cap": 4}, {"ta_cap": 0, "force_l1": 12}, {"force_l1": 0}):
     for k, val in opt.items():
         tb.set_option(k, val)
-    if opt:
-        F = tb.factorize(tb.Hankel(v, (n, n)))
+    F = tb.factorize(tb.Hankel(v, (n, n)))
     for _ in range(3):
         tb.mul_(y, F, x)
     torch.cuda.synchronize()
@@ -25,5 +24,4 @@ for opt in ({}, {"force_l1": 12}, {"force_l1": 12, "pipe_b": 1}, {"force_l1": 12
     for _ in range(10):
         tb.mul_(y, F, x)
     e1.record(); torch.cuda.synchronize()
-    print("total ms", round(e0.elapsed_time(e1) / 10, 4), end=" ")
-    print(opt, {k: round(1e3 * ms[k] / max(cnt[k], 1), 1) for k in ms if cnt[k]}, flush=True)
+    print("total ms", round(e0.elapsed_time(e1) / 10, 4), opt, {k: round(1e3 * ms[k] / max(cnt[k], 1), 1) for k in ms if cnt[k]}, flush=True)

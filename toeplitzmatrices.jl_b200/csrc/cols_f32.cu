@@ -8,6 +8,7 @@ namespace tb {
     case 916: return launch_cols_one<float, 9, 16, LAST>(a, s);                    \
     case 1016: return launch_cols_one<float, 10, 16, LAST>(a, s);                  \
     case 1108: return launch_cols_one<float, 11, 8, LAST>(a, s);                   \
+    case 1104: return launch_cols_one<float, 11, 4, LAST>(a, s);                   \
     case 1204: return launch_cols_one<float, 12, 4, LAST>(a, s);                   \
     default: return cudaErrorInvalidValue;                                         \
     }
