@@ -159,9 +159,65 @@ def test_largest_float64_embedding(tb):
     yo = O.matvec(O.Toeplitz(vc, vr), x, workers=-1)
     assert rel(y.cpu().numpy(), yo) <= 1e-12
     with pytest.raises(tb.ToeplitzB200Error):
-        z = torch.zeros(1 << 25, dtype=torch.float64, device="cuda")
-        z[0] = 1
-        tb.factorize(tb.SymmetricToeplitz(z))          # embedding 2^26 exceeds the Float64 plan: refused, no fallback
+        tb.factorize_empty_like(1, torch.float64, ((1 << 30) + 1, (1 << 30) + 1))    # embedding 2^32: beyond the three-level plan, refused
+
+
+@pytest.mark.parametrize("dtype,log2n", [("float64", 25), ("complex64", 26)])
+def test_three_level_plan(tb, dtype, log2n):
+    """Embeddings beyond the two-level limit (2^26 in Float64, 2^27 in Float32): N' = 2^9 x 2^(l-9), the rows are a
+    batched two-level transform on a child plan.  One vector against the oracle (reference FFT length m+n-1), a
+    three-column product (pair packing + odd tail) against single products, alpha/beta, and the adjoint-free
+    Circulant family at 2^26 / 2^27 points: eigvals == fft(vc), C * ldiv(C, b) == b."""
+    n = 1 << log2n
+    dt = np.dtype(dtype)
+    rng = np.random.default_rng(31)
+    cplx = dt.kind == "c"
+    mk = lambda k: (rng.standard_normal(k) + (1j * rng.standard_normal(k) if cplx else 0)).astype(dt)
+    vc, vr, x = mk(n), mk(n), mk(n)
+    vr[0] = vc[0]
+    A = tb.Toeplitz(torch.from_numpy(vc).cuda(), torch.from_numpy(vr).cuda())
+    F = tb.factorize(A)
+    xd = torch.from_numpy(x).cuda()
+    y = tb.mul(F, xd)
+    if dt == np.float64:
+        # the oracle proper: reference algorithm at its own FFT length m+n-1 on the host
+        yo = O.matvec(O.Toeplitz(vc, vr), x, workers=-1)
+    else:
+        # Float32 case at 2^27 points: an independent double-precision evaluation of the same circulant embedding on the
+        # device (torch.fft = cuFFT, test-side only) keeps the suite's run time in bounds
+        c = torch.zeros(2 * n, dtype=torch.complex128, device="cuda")
+        c[:n] = torch.from_numpy(vc).cuda()
+        c[n + 1:] = torch.from_numpy(vr[1:][::-1].copy()).cuda()
+        xp = torch.zeros(2 * n, dtype=torch.complex128, device="cuda")
+        xp[:n] = xd
+        yo = torch.fft.ifft(torch.fft.fft(c) * torch.fft.fft(xp))[:n].cpu().numpy()
+        del c, xp
+    PT.check("three-level mul n=2^%d %s" % (log2n, dtype), y.cpu().numpy(), yo, dt)
+    del yo
+    X3 = tb.colmajor(n, 3, xd.dtype)
+    X3[:, 0].copy_(xd); X3[:, 1].copy_(2 * xd); X3[:, 2].copy_(-xd)
+    Y3 = tb.colmajor(n, 3, xd.dtype)
+    Y3.fill_(1.0)
+    tb.mul_(Y3, F, X3, 0.5, 2.0)
+    for j, sc in enumerate((1.0, 2.0, -1.0)):
+        ref = 0.5 * sc * y + 2.0
+        assert float(torch.linalg.vector_norm(Y3[:, j] - ref) / torch.linalg.vector_norm(ref)) <= PT.ns_tol(dt), j
+    del F, A, X3, Y3, y
+    torch.cuda.empty_cache()
+    # Circulant with exactly 2^(log2n+1) points
+    nc = 2 * n
+    cd = np.complex128 if dt.itemsize * (1 if cplx else 2) == 16 else np.complex64
+    v = (0.9 ** np.arange(nc)).astype(cd)
+    v[1] += 0.25
+    C = tb.Circulant(torch.from_numpy(v).cuda())
+    FC = tb.factorize(C)
+    lam = tb.eigvals(FC).cpu().numpy()
+    lam_o = np.fft.fft(v.astype(np.complex128))
+    PT.check("three-level eigvals n=2^%d" % (log2n + 1), lam, lam_o, cd)
+    b = torch.from_numpy((rng.standard_normal(nc) + 1j * rng.standard_normal(nc)).astype(cd)).cuda()
+    xs = tb.ldiv(FC, b)
+    r = tb.mul(FC, xs)
+    assert float(torch.linalg.vector_norm(r - b) / torch.linalg.vector_norm(b)) <= PT.bound(cd, PT.cond_spectrum(lam_o))
 
 
 @pytest.mark.parametrize("n", [2, 3, 5, 16, 17, 33, 64, 65, 100, 128, 129, 200, 256, 257, 300, 384, 385, 500, 511, 512])

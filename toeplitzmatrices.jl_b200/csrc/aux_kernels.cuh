@@ -117,22 +117,29 @@ __global__ void k_spec_mul(cx<R>* __restrict__ out, const cx<R>* __restrict__ a,
 }
 
 // Natural-order spectrum out[k], k in [0, Np), from the private layout (eigvals,
-// src/linearalgebra.jl:286-287).  two_level: k = k1 + N1*k2, row p = pos1(k1).
+// src/linearalgebra.jl:286-287).  two_level: k = k1 + N1*k2, row p = pos1(k1); three-level (log2l0 > 0): k = k0 + N0*kr,
+// outer row pos0(k0), and kr addressed inside the row by the child plan's two levels.
 template <typename R>
 __global__ void k_unscramble(cx<R>* __restrict__ out, const cx<R>* __restrict__ spec, long long Np,
-                             int log2l1, int log2l2, int le) {
+                             int log2l0, int log2l1, int log2l2, int le) {
     PlanDims d2{log2l2, le};
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < Np;
          k += (long long)gridDim.x * blockDim.x) {
-        long long off;
+        long long off = 0, kr = k;
+        if (log2l0 > 0) {
+            PlanDims d0{log2l0, le};
+            const int k0 = (int)(k & ((1LL << log2l0) - 1));
+            kr = k >> log2l0;
+            off = (long long)d0.pos_of_freq(k0) << (log2l1 + log2l2);
+        }
         if (log2l1 == 0) {
-            off = d2.layout_of_pos(d2.pos_of_freq((int)k));
+            off += d2.layout_of_pos(d2.pos_of_freq((int)kr));
         } else {
             PlanDims d1{log2l1, le};
-            const int k1 = (int)(k & ((1LL << log2l1) - 1));
-            const int k2 = (int)(k >> log2l1);
+            const int k1 = (int)(kr & ((1LL << log2l1) - 1));
+            const int k2 = (int)(kr >> log2l1);
             const long long p = d1.pos_of_freq(k1);
-            off = (p << log2l2) + d2.layout_of_pos(d2.pos_of_freq(k2));
+            off += (p << log2l2) + d2.layout_of_pos(d2.pos_of_freq(k2));
         }
         out[k] = spec[off];
     }

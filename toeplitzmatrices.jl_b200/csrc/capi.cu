@@ -273,6 +273,10 @@ struct tb200_fact {
     int kind = 0, dtype = 0, prec = 0, a_real = 0, device = 0;
     int64_t m = 0, n = 0, Np = 0;
     int log2np = 0, two_level = 0, log2l1 = 0, log2l2 = 0, ta = 0;
+    // three-level plan (embeddings beyond the two-level limit): an outer strided pass of 2^log2l1 points around a
+    // batched two-level transform of the 2^log2l2-point rows, which lives in the child handle `inner`
+    int three_level = 0;
+    std::shared_ptr<tb200_fact> inner;
     int reverse_x = 0;
     static constexpr int MAXS = StreamWork::MAXS;
     std::shared_ptr<DevBuf> spec, inv_spec, tw_lo, tw_hi, tw_g;
@@ -334,9 +338,39 @@ static int make_plan(tb200_fact* h) {
     int l2 = l - l1;
     const int l1max = 12;                                    // 2^12 x 2^13 (Float64, 2 columns per tile) / 2^12 x 2^14 (Float32)
     if (l1 > l1max) { l1 = l1max; l2 = l - l1; }
-    if (l2 > (h->prec ? 13 : 14))
-        return set_error(TB200_UNSUPPORTED, "embedding length 2^%d exceeds the two-level plan (max 2^%d)", l,
-                         l1max + (h->prec ? 13 : 14));
+    if (l2 > (h->prec ? 13 : 14)) {
+        // beyond the two-level plan: N' = 2^9 x 2^(l-9); the rows are themselves two-level transforms (child plan)
+        const int lo = 9, lr = l - lo;
+        if (l > 30 || lr > l1max + (h->prec ? 13 : 14))
+            return set_error(TB200_UNSUPPORTED, "embedding length 2^%d exceeds the three-level plan (max 2^30)", l);
+        h->three_level = 1; h->two_level = 1; h->log2l1 = lo; h->log2l2 = lr;
+        h->ta = 128 / (int)(h->prec ? 16 : 8);
+        std::shared_ptr<tb200_fact> child(new tb200_fact());
+        child->kind = TB200_CIRCULANT; child->dtype = h->prec ? TB200_C64 : TB200_C32; child->prec = h->prec; child->a_real = 0;
+        child->device = h->device; child->m = child->n = child->Np = 1ll << lr; child->log2np = lr;
+        TB_TRY(make_plan(child.get()));
+        h->inner = child;
+        h->tw_hb = (l + 1) / 2;
+        const long long nlo3 = 1ll << h->tw_hb, nhi3 = 1ll << (l - h->tw_hb);
+        if (h->prec) {
+            std::vector<cx<double>> lo_t, hi_t;
+            fill_twiddles<double>(lo_t, nlo3, 1, 1ll << l);
+            fill_twiddles<double>(hi_t, nhi3, nlo3, 1ll << l);
+            TB_TRY(dev_alloc_sync(h->tw_lo, lo_t.size() * 16, "level twiddles"));
+            TB_TRY(dev_alloc_sync(h->tw_hi, hi_t.size() * 16, "level twiddles"));
+            TB_TRY(upload_sync(h->tw_lo->p, lo_t.data(), lo_t.size() * 16, "level twiddle upload"));
+            TB_TRY(upload_sync(h->tw_hi->p, hi_t.data(), hi_t.size() * 16, "level twiddle upload"));
+        } else {
+            std::vector<cx<float>> lo_t, hi_t;
+            fill_twiddles<float>(lo_t, nlo3, 1, 1ll << l);
+            fill_twiddles<float>(hi_t, nhi3, nlo3, 1ll << l);
+            TB_TRY(dev_alloc_sync(h->tw_lo, lo_t.size() * 8, "level twiddles"));
+            TB_TRY(dev_alloc_sync(h->tw_hi, hi_t.size() * 8, "level twiddles"));
+            TB_TRY(upload_sync(h->tw_lo->p, lo_t.data(), lo_t.size() * 8, "level twiddle upload"));
+            TB_TRY(upload_sync(h->tw_hi->p, hi_t.data(), hi_t.size() * 8, "level twiddle upload"));
+        }
+        return TB200_OK;                               // no [E][N2] table at this N2: the passes use the split tables per element
+    }
     if (l1 < 6) { l1 = 6; l2 = l - l1; }
     if (g_force_l1.load() >= 6 && l - g_force_l1.load() >= 4 && l - g_force_l1.load() <= (h->prec ? 13 : 14)) { l1 = g_force_l1.load(); l2 = l - l1; }
     const int full = 128 / (int)(h->prec ? 16 : 8);            // columns per 128-byte line
@@ -484,6 +518,9 @@ struct ConvCall {
     double scale = 1.0; double alpha[2] = {1, 0}, beta[2] = {0, 0}; int has_beta = 0;
     const int* colmap = nullptr;                    // device: user column of logical column j (NULL = identity)
     const double* col_alpha = nullptr; int col_alpha_stride = 0;   // device: per-user-column factor on alpha
+    // the slots are the rows of an outer (three-level) transform: every slot has its own spectrum segment, and
+    // forward-only / inverse-only calls run all of them (layout-order data is addressed slot by slot)
+    int nested = 0;
 };
 
 // 3-D tensor map over a column-major matrix seen as [column][row of N2 elements][N2 elements], in 8-byte units
@@ -510,8 +547,11 @@ static bool make_cols_tensor_map(CUtensorMap* map, const void* base, int units_p
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+template <typename R> static int run_conv3_t(tb200_fact* h, const ConvCall& c, cudaStream_t s);
+
 template <typename R>
 static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
+    if (h->three_level) return run_conv3_t<R>(h, c, s);
     ConvArgs<R> a;
     memset(&a, 0, sizeof(a));
     const cx<R>* tw_rows = nullptr;
@@ -689,15 +729,21 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
             pb.ldx = N2; pb.ldy = N2;
             pb.x = scratch; pb.x_mode = IO_CPLX; pb.y = scratch; pb.y_mode = IO_CPLX;
             pb.spec_rows = (int)N1;
+            if (c.nested && pb.spec) {   // rows of an outer transform: slot f owns the spectrum segment f
+                pb.spec = pb.spec + (size_t)f0 * Np;
+                pb.spec_rows = (int)(g * N1);
+            }
             pb.scale = (R)1; pb.alpha = mk<R>(1, 0); pb.beta = mk<R>(0, 0); pb.has_beta = 0;
             pb.colmap = nullptr; pb.col_alpha = nullptr;
             if (!c.do_fwd) {             // inverse only: rows come from a layout-order spectrum
-                pb.x = c.x; pb.x_mode = IO_SPEC; pb.spec = nullptr;
-                if (g != 1 || c.nfft != 1) return set_error(TB200_BAD_ARG, "internal: inverse-only runs one transform");
+                pb.x = c.nested ? (const void*)(reinterpret_cast<const cx<R>*>(c.x) + (size_t)f0 * Np) : c.x;
+                pb.x_mode = IO_SPEC; pb.spec = nullptr;
+                if (!c.nested && (g != 1 || c.nfft != 1)) return set_error(TB200_BAD_ARG, "internal: inverse-only runs one transform");
             }
             if (!c.do_inv) {             // forward only: rows go out in layout order
-                pb.y = c.y; pb.y_mode = IO_SPEC; pb.spec = nullptr;
-                if (g != 1 || c.nfft != 1) return set_error(TB200_BAD_ARG, "internal: forward-only runs one transform");
+                pb.y = c.nested ? (void*)(reinterpret_cast<cx<R>*>(c.y) + (size_t)f0 * Np) : c.y;
+                pb.y_mode = IO_SPEC; pb.spec = nullptr;
+                if (!c.nested && (g != 1 || c.nfft != 1)) return set_error(TB200_BAD_ARG, "internal: forward-only runs one transform");
             }
             pb.pdl = (use_pdl && c.do_fwd) ? 1 : 0;          // behind pass A of this group
             count_launch();
@@ -721,6 +767,71 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
         for (int i = 0; i < nstr; ++i) {
             TB_CUDA(cudaEventRecord(w->ev_join[i], w->hs[i]), "join");
             TB_CUDA(cudaStreamWaitEvent(user_stream, w->ev_join[i], 0), "join");
+        }
+    }
+    return TB200_OK;
+}
+
+// Three-level transform: N' = N0 x Nr.  Per FFT slot: the outer strided pass (k_colsA, N0-point columns at stride Nr)
+// fills a workspace of N' points; its N0 rows are then ONE batched call of the two-level machinery on the child plan
+// (forward -> x spectrum segment of the row -> inverse, in place, column groups / overlap streams / L2 window as for
+// any batch); the outer inverse pass (k_colsC) applies the epilogue.  Forward-only (factorize) and inverse-only
+// (spectrum -> coefficients) calls run the matching halves.
+template <typename R>
+static int run_conv3_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
+    if (c.nfft <= 0) return TB200_OK;
+    if (c.colmap || c.col_alpha) return set_error(TB200_UNSUPPORTED, "column selection is not available on the three-level plan");
+    tb200_fact* hi = h->inner.get();
+    const long long Np = h->Np, N0 = 1ll << h->log2l1, Nr = 1ll << h->log2l2;
+    const cx<R>* tw_cols = nullptr;
+    TB_TRY(stage_twiddles<R>(h->log2l1, &tw_cols));
+    TB_TRY(wait_spectrum(h, c.spec, s));
+    StreamWork* w = h->work_for(s);
+    TB_TRY(ensure_buf(w->scratch, (size_t)Np * sizeof(cx<R>), "outer workspace", s));
+    cx<R>* W = reinterpret_cast<cx<R>*>(w->scratch->p);
+    ConvArgs<R> a;
+    memset(&a, 0, sizeof(a));
+    a.x = c.x; a.ldx = c.ldx; a.x_mode = c.x_mode; a.n_in = c.n_in; a.reverse_x = c.reverse_x;
+    a.y = c.y; a.ldy = c.ldy; a.y_mode = c.y_mode; a.m_out = c.m_out;
+    a.ncols = c.ncols; a.nfft = 1;
+    a.do_fwd = c.do_fwd; a.do_inv = c.do_inv;
+    a.scale = (R)c.scale; a.alpha = mk<R>((R)c.alpha[0], (R)c.alpha[1]); a.beta = mk<R>((R)c.beta[0], (R)c.beta[1]);
+    a.has_beta = c.has_beta;
+    a.tw = tw_cols;
+    a.scratch = W;
+    a.log2n2 = h->log2l2;
+    a.tw_lo = reinterpret_cast<const cx<R>*>(h->tw_lo->p);
+    a.tw_hi = reinterpret_cast<const cx<R>*>(h->tw_hi->p);
+    a.tw_hb = h->tw_hb;
+    a.tw_g = nullptr;
+    const size_t in_esz = (c.x_mode == IO_REAL || c.x_mode == IO_PAIR) ? sizeof(R) : sizeof(cx<R>);
+    const size_t out_esz = (c.y_mode == IO_REAL || c.y_mode == IO_PAIR) ? sizeof(R) : sizeof(cx<R>);
+    const long long cols_per_fft = (c.x_mode == IO_PAIR || c.y_mode == IO_PAIR) ? 2 : 1;
+    if ((!c.do_fwd || !c.do_inv) && c.nfft != 1) return set_error(TB200_BAD_ARG, "internal: one-directional runs take one transform");
+    for (long long f = 0; f < c.nfft; ++f) {
+        if (c.do_fwd) {
+            ConvArgs<R> pa = a;
+            pa.ncols = c.ncols - f * cols_per_fft;
+            pa.x = reinterpret_cast<const char*>(c.x) + (size_t)f * cols_per_fft * c.ldx * in_esz;
+            count_launch();
+            PassTimer pt(0, s);
+            TB_CUDA(launch_colsA<R>(h->log2l1, h->ta, pa, s), "k_colsA (outer)");
+        }
+        ConvCall ci;
+        ci.x = c.do_fwd ? (const void*)W : c.x; ci.ldx = Nr; ci.x_mode = IO_CPLX; ci.n_in = Nr;
+        ci.y = c.do_inv ? (void*)W : c.y; ci.ldy = Nr; ci.y_mode = IO_CPLX; ci.m_out = Nr;
+        ci.ncols = N0; ci.nfft = N0;
+        ci.spec = (c.do_fwd && c.do_inv) ? c.spec : nullptr;
+        ci.do_fwd = c.do_fwd; ci.do_inv = c.do_inv;
+        ci.nested = 1;
+        TB_TRY(run_conv_t<R>(hi, ci, s));
+        if (c.do_inv) {
+            ConvArgs<R> pc = a;
+            pc.ncols = c.ncols - f * cols_per_fft;
+            pc.y = reinterpret_cast<char*>(c.y) + (size_t)f * cols_per_fft * c.ldy * out_esz;
+            count_launch();
+            PassTimer pt(2, s);
+            TB_CUDA(launch_colsC<R>(h->log2l1, h->ta, pc, s), "k_colsC (outer)");
         }
     }
     return TB200_OK;
@@ -1220,9 +1331,12 @@ int tb200_circ_spectrum(tb200_handle_t h, void* out, void* stream) {
     TB_TRY(wait_spectrum(h, nullptr, s));
     if (h->bluestein)
         return cuda_status(cudaMemcpyAsync(out, h->spec->p, (size_t)h->n * (h->prec ? 16 : 8), cudaMemcpyDeviceToDevice, s), "spectrum copy");
-    const int l1 = h->two_level ? h->log2l1 : 0;
-    if (h->prec) k_unscramble<double><<<ew_grid(h->Np), 256, 0, s>>>((cx<double>*)out, (const cx<double>*)h->spec->p, h->Np, l1, h->log2l2, le_of<double>());
-    else k_unscramble<float><<<ew_grid(h->Np), 256, 0, s>>>((cx<float>*)out, (const cx<float>*)h->spec->p, h->Np, l1, h->log2l2, le_of<float>());
+    // three-level: outer digit k0 (2^log2l1 points), then the child plan's two levels inside each row
+    const int l0 = h->three_level ? h->log2l1 : 0;
+    const tb200_fact* pl = h->three_level ? h->inner.get() : h;
+    const int l1 = pl->two_level ? pl->log2l1 : 0;
+    if (h->prec) k_unscramble<double><<<ew_grid(h->Np), 256, 0, s>>>((cx<double>*)out, (const cx<double>*)h->spec->p, h->Np, l0, l1, pl->log2l2, le_of<double>());
+    else k_unscramble<float><<<ew_grid(h->Np), 256, 0, s>>>((cx<float>*)out, (const cx<float>*)h->spec->p, h->Np, l0, l1, pl->log2l2, le_of<float>());
     count_launch();
     return cuda_status(cudaGetLastError(), "k_unscramble");
 }
@@ -1462,7 +1576,8 @@ static int krylov_batched_t(bool is_cg, tb200_fact* A, tb200_fact* M, T* X, int6
     const size_t vsz = (size_t)n * (size_t)chunk;
     T* w = (T*)work->p;
     // column selection needs the pow2 kernels on both operators (a Bluestein plan runs every column)
-    const bool can_select = !A->bluestein && !(M && M->bluestein);
+    // column selection / per-column alpha live in the two-level passes; chirp-z and three-level plans take the unfused route
+    const bool can_select = !A->bluestein && !A->three_level && !(M && (M->bluestein || M->three_level));
     auto finish = [&](int status) {                     // temporaries are stream-ordered: drain before they go
         cudaStreamSynchronize(s);
         return status;
@@ -1546,7 +1661,7 @@ static int krylov_batched_t(bool is_cg, tb200_fact* A, tb200_fact* M, T* X, int6
                     k_bcgs_q<T><<<gew, 256, 0, s>>>(q, uh, u, vh, st, n, n, cm);                            // :185-188
                     count_launch();
                     TB_KTRY(precond(uh, uh, na));                                                           // :189
-                    if (!A->bluestein) {
+                    if (!A->bluestein && !A->three_level) {
                         k_bx<T><<<gew, 256, 0, s>>>(Xc, ldx, uh, st, n, n, cm);                             // :192-194
                         count_launch();
                         TB_KTRY(mulA(r, uh, n, na, minus, one, false, true));                               // :196  r -= alpha_j * A * uh

@@ -218,6 +218,11 @@ __device__ __forceinline__ cx<R> level_twiddle(const ConvArgs<R>& p, unsigned m)
 
 template <typename R, class F>
 __device__ __forceinline__ void level_twiddles(const ConvArgs<R>& p, int t, int j2, cx<R>* w) {
+    if (!p.tw_g) {            // outer pass of a three-level plan: N2 is far too long for the [E][N2] table
+#pragma unroll
+        for (int i = 0; i < F::E; ++i) w[i] = level_twiddle<R>(p, (unsigned)F::freq_of_pos(F::pos_of_reg(i, t)) * (unsigned)j2);
+        return;
+    }
     const unsigned kbase = (unsigned)F::freq_of_pos(F::pos_of_reg(0, t));
     const cx<R> base = level_twiddle<R>(p, kbase * (unsigned)j2);
     // delta_i is linear in the bits of i (pos_of_reg and freq_of_pos move disjoint bit fields), so the E factors
