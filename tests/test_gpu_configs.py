@@ -218,6 +218,17 @@ def test_three_level_plan(tb, dtype, log2n):
     xs = tb.ldiv(FC, b)
     r = tb.mul(FC, xs)
     assert float(torch.linalg.vector_norm(r - b) / torch.linalg.vector_norm(b)) <= PT.bound(cd, PT.cond_spectrum(lam_o))
+    del FC, C, xs, r, b
+    torch.cuda.empty_cache()
+    if dt == np.float64:
+        # cgs + Strang on a three-level operator (the Krylov driver takes its unfused route there): true residual
+        vk = torch.from_numpy(0.5 ** np.arange(n)).cuda()
+        S = tb.SymmetricToeplitz(vk)
+        bb = torch.from_numpy(rng.standard_normal(n)).cuda()
+        xk, err, it, flag = tb.cgs(S, torch.zeros_like(bb), bb, tb.factorize(tb.strang(S)), 20, 1e-13)
+        assert flag == 0 and it <= 6, (flag, it, err)
+        rr = bb - tb.mul(S, xk)
+        assert float(torch.linalg.vector_norm(rr) / torch.linalg.vector_norm(bb)) <= 1e-12
 
 
 @pytest.mark.parametrize("n", [2, 3, 5, 16, 17, 33, 64, 65, 100, 128, 129, 200, 256, 257, 300, 384, 385, 500, 511, 512])
