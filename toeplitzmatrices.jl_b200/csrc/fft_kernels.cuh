@@ -56,7 +56,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 // Inter-level twiddles of one thread (fixed column j2): w^(k1(i) j2) = w^(kbase(t) j2) * w^(delta_i j2).
 // One split-table lookup for the base, LOGE coalesced loads from the [E][N2] table, E-1 complex multiplies.
-template <typename R, class F>
+template <typename R, class F, bool GTAB = true>
 __device__ __forceinline__ void level_twiddles(const ConvArgs<R>& p, int t, int j2, cx<R>* w);
 
 // ---- per-slot input / output views: the embedding (zero pad, Hankel reversal), the packing of
@@ -216,9 +216,12 @@ __device__ __forceinline__ cx<R> level_twiddle(const ConvArgs<R>& p, unsigned m)
     return cmul(lo, hi);
 }
 
-template <typename R, class F>
+// GTAB = false: outer pass of a three-level plan, where N2 is far too long for the [E][N2] table -- every factor comes
+// from the split tables.  A compile-time choice: as a run-time branch it cost the two-level kernels 56 bytes of spills
+// and 6 % of the headline rate.
+template <typename R, class F, bool GTAB>
 __device__ __forceinline__ void level_twiddles(const ConvArgs<R>& p, int t, int j2, cx<R>* w) {
-    if (!p.tw_g) {            // outer pass of a three-level plan: N2 is far too long for the [E][N2] table
+    if constexpr (!GTAB) {
 #pragma unroll
         for (int i = 0; i < F::E; ++i) w[i] = level_twiddle<R>(p, (unsigned)F::freq_of_pos(F::pos_of_reg(i, t)) * (unsigned)j2);
         return;
@@ -240,7 +243,7 @@ __device__ __forceinline__ void level_twiddles(const ConvArgs<R>& p, int t, int 
 
 // grid.x = (N2/TA) * nfft ; block = TA * NT1.  HALF: the input occupies at most the first half of the embedding
 // (n <= N'/2, every Toeplitz/Hankel product), so rows >= N1/2 are padding: not loaded, first butterfly level pruned.
-template <typename R, int LOG2L1, int TA, bool HALF>
+template <typename R, int LOG2L1, int TA, bool HALF, bool GTAB = true>
 __global__ void __launch_bounds__((1 << (LOG2L1 - le_of<R>())) * TA, min_ctas<R>((1 << (LOG2L1 - le_of<R>())) * TA, (int)sizeof(cx<R>) * (1 << LOG2L1) * TA))
 k_colsA(const ConvArgs<R> p) {
     using F = SlotFFT<R, LOG2L1>;
@@ -263,14 +266,14 @@ k_colsA(const ConvArgs<R> p) {
     F::template forward<ColMap<TA>, false, HALF>(a, t, sm, map, p.tw);
     cx<R>* out = p.scratch + (f << (l2 + LOG2L1)) + j2;
     cx<R> w[E];
-    level_twiddles<R, F>(p, t, j2, w);
+    level_twiddles<R, F, GTAB>(p, t, j2, w);
 #pragma unroll
     for (int i = 0; i < E; ++i) out[(long long)F::pos_of_reg(i, t) << l2] = cmul(a[i], w[i]);
 }
 
 // HALF: only the first half of the embedding is wanted (m <= N'/2): outputs j >= E/2 are never stored and the
 // compiler drops the second half of the last butterfly level.
-template <typename R, int LOG2L1, int TA, bool HALF>
+template <typename R, int LOG2L1, int TA, bool HALF, bool GTAB = true>
 __global__ void __launch_bounds__((1 << (LOG2L1 - le_of<R>())) * TA, min_ctas<R>((1 << (LOG2L1 - le_of<R>())) * TA, (int)sizeof(cx<R>) * (1 << LOG2L1) * TA))
 k_colsC(const ConvArgs<R> p) {
     using F = SlotFFT<R, LOG2L1>;
@@ -287,7 +290,7 @@ k_colsC(const ConvArgs<R> p) {
     cx<R> a[E];
     {
         cx<R> w[E];
-        level_twiddles<R, F>(p, t, j2, w);      // tables only: may run before the previous pass has finished
+        level_twiddles<R, F, GTAB>(p, t, j2, w);      // tables only: may run before the previous pass has finished
         pdl_wait();
 #pragma unroll
         for (int i = 0; i < E; ++i) a[i] = cmulc(ld_stream(in + ((long long)F::pos_of_reg(i, t) << l2)), w[i]);

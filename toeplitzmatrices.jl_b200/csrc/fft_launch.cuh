@@ -74,10 +74,28 @@ cudaError_t launch_cols_one(const ConvArgs<R>& a, cudaStream_t s) {
     return launch_cols_v<R, LOG2L1, TA, LAST, false>(a, s);
 }
 
+// the outer passes of the three-level plan (no [E][N2] twiddle table) exist for its one column length, 2^9
 template <typename R, int LOG2L1, int TA, bool LAST, bool HALF>
 cudaError_t launch_cols_v(const ConvArgs<R>& a, cudaStream_t s) {
     constexpr int threads = (1 << (LOG2L1 - le_of<R>())) * TA;
     constexpr size_t smem = sizeof(cx<R>) * (size_t)(1 << LOG2L1) * TA;
+    if constexpr (LOG2L1 == 9 && TA == 128 / (int)sizeof(cx<R>)) {
+        if (!a.tw_g) {
+            auto kern3 = LAST ? k_colsC<R, LOG2L1, TA, HALF, false> : k_colsA<R, LOG2L1, TA, HALF, false>;
+            static bool configured3[64] = {};
+            int dev3 = 0;
+            cudaGetDevice(&dev3);
+            if (!configured3[dev3 & 63]) {
+                cudaError_t e = cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                configured3[dev3 & 63] = true;
+            }
+            const long long tiles3 = (1LL << a.log2n2) / TA;
+            return launch_pass(kern3, (unsigned)(tiles3 * a.nfft), threads, smem, s, a);
+        }
+    } else {
+        if (!a.tw_g) return cudaErrorInvalidValue;
+    }
     auto kern = LAST ? k_colsC<R, LOG2L1, TA, HALF> : k_colsA<R, LOG2L1, TA, HALF>;
     static bool configured[64] = {};          // the attribute is per device
     int dev = 0;
