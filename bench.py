@@ -646,6 +646,18 @@ def run_ours(args):
                 "timed_how": "CUDA events around every pass on its launching stream, second K-step region, overlap off",
                 "whole_step_frac": ALG_BYTES_PER_MATVEC * ncols / (ms / args.steps * 1e-3) / 1e9 / peak,
                 "co_bound": "FP64 FMA pipe: ~210 MFLOP per matvec (SURVEY 8d)"}
+    # the second fraction -- DRAM bytes the kernel really moves (committed ncu counters) per second of its
+    # launch, against the same peak; "cold" = every launch starts with a flushed L2 (ncu default), "warm" = as in the loop
+    try:
+        tjw = json.load(open(tpath)).get("warm", {})
+        if traffic and per_launch_ms > 0:
+            roofline["dram_fraction"] = {"cold": traffic / (per_launch_ms * 1e-3) / 1e9 / peak,
+                                         "warm": (tjw.get(dom, 0) / (per_launch_ms * 1e-3) / 1e9 / peak) if tjw.get(dom) else None,
+                                         "warm_bytes_per_pair_all_passes": tjw.get("pair_total"),
+                                         "alg_bytes_per_pair": 2 * ALG_BYTES_PER_MATVEC,
+                                         "source": "static ncu counters (profiles/traffic.json) over this run's launch time"}
+    except Exception:
+        pass
     fp64_flop_per_matvec = 5.0 * (2 * n) * math.log2(2 * n)
     fp64_tflops = fp64_flop_per_matvec * ncols / (ms / args.steps * 1e-3) / 1e12
     roofline["fp64"] = {"flop_per_matvec": fp64_flop_per_matvec, "achieved_tflops": fp64_tflops, "peak_tflops": FP64_PEAK_TFLOPS,
