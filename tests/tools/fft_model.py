@@ -56,6 +56,8 @@ class Slot:
     def pos_of_reg(self, i, t):
         if self.rem == 0:
             return t * E + brev(i, LOGE)
+        if self.rem == 1:       # cross-lane radix-2 (SlotFFT::REM_SHFL): positions P and P^1 sit in threads t and t^1
+            return ((t >> 1) << (1 + LOGE)) + (t & 1) + (brev(i, LOGE) << 1)
         return (t + (i // self.RR) * self.NT) * self.RR + brev(i % self.RR, self.rem)
 
     def freq_of_pos(self, P):
@@ -80,6 +82,9 @@ class Slot:
         if self.rem == 0:
             t, c = P >> LOGE, P & (E - 1)
             return brev(c, LOGE) * self.NT + t
+        if self.rem == 1:
+            g, c, r = P >> (1 + LOGE), (P >> 1) & (E - 1), P & 1
+            return brev(c, LOGE) * self.NT + ((g << 1) | r)
         b, c = P >> self.rem, P & (self.RR - 1)
         t, u = b % self.NT, b // self.NT
         return (u * self.RR + brev(c, self.rem)) * self.NT + t
@@ -103,14 +108,16 @@ class Slot:
                     for c in range(1, E):
                         a[brev(c, LOGE)] *= np.exp(-2j * np.pi * (r * c) / (E * s))
                 regs[t] = a
-            last = (k == self.nfull - 1) and self.rem == 0
+            last = (k == self.nfull - 1) and self.rem in (0, 1)
             if not last:
                 for t in range(NT):
                     g, r = t >> ls, t & (s - 1)
                     base = (g << (ls + LOGE)) + r
                     for c in range(E):
                         sm[base + c * s] = regs[t][brev(c, LOGE)]
-        if self.rem:
+        if self.rem == 1:
+            regs = self._rem_shuffle(regs)
+        elif self.rem:
             RR = self.RR
             for t in range(NT):
                 a = [0] * E
@@ -121,11 +128,21 @@ class Slot:
                 regs[t] = a
         return regs
 
+    def _rem_shuffle(self, regs):
+        """the radix-2 level between threads t and t^1: even keeps mine + partner, odd keeps partner - mine"""
+        out = []
+        for t in range(self.NT):
+            mine, other = regs[t], regs[t ^ 1]
+            out.append([(other[i] - mine[i]) if (t & 1) else (mine[i] + other[i]) for i in range(E)])
+        return out
+
     def inverse(self, regs):
         L, NT = self.L, self.NT
         sm = np.zeros(L, dtype=complex)
         regs = [list(r) for r in regs]
-        if self.rem:
+        if self.rem == 1:
+            regs = self._rem_shuffle(regs)
+        elif self.rem:
             RR = self.RR
             for t in range(NT):
                 for u in range(E // RR):
@@ -136,7 +153,7 @@ class Slot:
         for k in range(self.nfull - 1, -1, -1):
             ls = self.log2l - LOGE * (k + 1)
             s = 1 << ls
-            first = (k == self.nfull - 1) and self.rem == 0
+            first = (k == self.nfull - 1) and self.rem in (0, 1)
             for t in range(NT):
                 g, r = t >> ls, t & (s - 1)
                 base = (g << (ls + LOGE)) + r

@@ -245,10 +245,28 @@ struct SlotFFT {
     static constexpr int REM = LOG2L % LOGE;
     static constexpr int RR = 1 << REM;
 
+    // A one-bit remainder (L = E^k * 2) is not given a shared-memory exchange of its own: the last radix-2 level pairs
+    // positions P and P^1, which after the last full stage sit in threads t and t^1 -- the same warp -- so it is done
+    // with one shuffle per register (half the shared-memory-pipe wavefronts of a store + load, and no barrier).
+    static constexpr bool REM_SHFL = (REM == 1);
     // position (in the digit-reversed output order) of register i of thread t
     __host__ __device__ static constexpr int pos_of_reg(int i, int t) {
         return REM == 0 ? t * E + brev(i, LOGE)
+             : REM_SHFL ? ((t >> 1) << (1 + LOGE)) + (t & 1) + (brev(i, LOGE) << 1)
                         : (t + (i / RR) * NT) * RR + brev(i % RR, REM);
+    }
+    // the cross-lane radix-2 level (its own inverse up to the factor 2 the caller's 1/N carries)
+    template <class Map>
+    __device__ __forceinline__ static void rem_shuffle(cx<R>* a, int t) {
+        constexpr int LM = 1 << Map::TSHIFT;             // lane distance of thread t ^ 1
+        const bool odd = (t & 1) != 0;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            cx<R> v;
+            v.x = __shfl_xor_sync(0xffffffffu, a[i].x, LM);
+            v.y = __shfl_xor_sync(0xffffffffu, a[i].y, LM);
+            a[i] = odd ? csub(v, a[i]) : cadd(a[i], v);
+        }
     }
     // frequency index held at position P
     __host__ __device__ static constexpr int freq_of_pos(int P) {
@@ -289,7 +307,7 @@ struct SlotFFT {
 #pragma unroll
                 for (int c = 1; c < E; ++c) a[brev(c, LOGE)] = cmul(a[brev(c, LOGE)], w[c]);
             }
-            const bool last = (k == NFULL - 1) && (REM == 0);
+            const bool last = (k == NFULL - 1) && (REM == 0 || REM_SHFL);
             if (!last) {
 #pragma unroll
                 for (int c = 0; c < E; ++c) TB_SM_STORE(sm[map.at(pre, c << ls)], a[brev(c, LOGE)]);
@@ -297,7 +315,9 @@ struct SlotFFT {
                 else __syncthreads();
             }
         }
-        if (REM > 0) {
+        if constexpr (REM_SHFL) {
+            rem_shuffle<Map>(a, t);
+        } else if (REM > 0) {
 #pragma unroll
             for (int u = 0; u < E / RR; ++u) {
                 const int pre = map.pre((t + u * NT) * RR);
@@ -313,7 +333,9 @@ struct SlotFFT {
     template <class Map>
     __device__ __forceinline__ static void inverse(cx<R>* a, int t, cx<R>* sm, Map map,
                                                    const cx<R>* __restrict__ tw) {
-        if (REM > 0) {
+        if constexpr (REM_SHFL) {
+            rem_shuffle<Map>(a, t);
+        } else if (REM > 0) {
 #pragma unroll
             for (int u = 0; u < E / RR; ++u) dit_regs<R, RR>(a + u * RR);
 #pragma unroll
@@ -330,7 +352,7 @@ struct SlotFFT {
             const int s = 1 << ls;
             const int g = t >> ls, r = t & (s - 1);
             const int pre = map.pre((g << (ls + LOGE)) + r);
-            const bool first = (k == NFULL - 1) && (REM == 0);
+            const bool first = (k == NFULL - 1) && (REM == 0 || REM_SHFL);
             if (!first) {
 #pragma unroll
                 for (int c = 0; c < E; ++c) TB_SM_LOAD(a[brev(c, LOGE)], sm[map.at(pre, c << ls)]);
@@ -362,6 +384,7 @@ struct PlanDims {
     __host__ __device__ int pos_of_reg(int i, int t) const {
         const int E = 1 << LOGE;
         int rm = rem(), rr = 1 << rm;
+        if (rm == 1) return ((t >> 1) << (1 + LOGE)) + (t & 1) + (brev(i, LOGE) << 1);      // cross-lane radix-2 (SlotFFT::REM_SHFL)
         return rm == 0 ? t * E + brev(i, LOGE) : (t + (i / rr) * NT()) * rr + brev(i % rr, rm);
     }
     __host__ __device__ int freq_of_pos(int P) const {
@@ -392,6 +415,10 @@ struct PlanDims {
         if (rm == 0) {
             int t = P >> LOGE, c = P & (E - 1);
             return brev(c, LOGE) * nt + t;
+        }
+        if (rm == 1) {
+            const int g = P >> (1 + LOGE), c = (P >> 1) & (E - 1), r = P & 1;
+            return brev(c, LOGE) * nt + ((g << 1) | r);
         }
         int b = P >> rm, c = P & (rr - 1);
         int t = b % nt, u = b / nt;
