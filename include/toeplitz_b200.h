@@ -215,6 +215,17 @@ int tb200_vec_equal(int64_t n, const void* a, int dtype_a, const void* b, int dt
 
 /* tuning / introspection: number of kernel launches issued by this library so far      */
 int64_t tb200_launch_count(void);
+/* process-wide tuning knobs (defaults are what the measurements in DESIGN.md were taken with):
+ *   "group_bytes"      two-level workspace budget per column group (default 32 MiB)
+ *   "overlap_streams"  internal streams that alternate column groups (default 2; 0 / 1 = off)
+ *   "l2_persist_mb"    persisting-L2 carve-out for the workspaces of overlapped products (default 64; 0 = off)
+ *   "prune_half"       skip the padding half of the embedding in the strided passes (default 1)
+ *   "pdl"              programmatic dependent launch of passes B / C: 0 off, 1 products without group overlap (default), 2 always
+ *   "tma"              TMA tensor-box staging of the strided tiles: bit 0 pass A, bit 1 pass C (default 0)
+ *   "lev_gen"          Levinson / Durbin in generator form (default 1; 0 = the dot-product kernels)
+ *   "time_passes"      bracket every pass with CUDA events for tb200_pass_times (default 0)
+ *   "single_max_f64/f32", "l2max_f64/f32", "force_l1", "ta_cap"   plan shape overrides (experiments)
+ *   "host_chunk_bytes", "krylov_work_bytes"                       staging / workspace budgets of tb200_mul_host and the batched solvers */
 int tb200_set_option(const char* name, int64_t value);
 /* with option "time_passes" = 1 every FFT pass is bracketed by CUDA events on its stream;
  * this drains them: summed milliseconds and launch counts for {cols A, rows B, cols C,
