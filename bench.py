@@ -530,6 +530,15 @@ def run_ours(args):
     parity_rank = rel_err(Y[:, pcols].cpu().numpy(), Yo)
     # checksum of the whole batch against a second product of the same inputs through the single-stream path
     parity_all = max_over_ranks(parity_rank, dist, world)
+    # every column of the full-size batch at once, by linearity: (A X) w == A (X w) for a seeded random weight vector w
+    # (distinct weights, so a column permutation or a dropped column shows up as an O(1) error); the right-hand side is
+    # one more product through the library, so the check costs one matvec plus two passes over X and Y
+    w = torch.randn(ncols, dtype=torch.float64, device="cuda", generator=g)
+    yw = tb.mul(F, torch.mv(X, w))
+    Yw = torch.mv(Y, w)
+    lin_rank = float(torch.linalg.vector_norm(Yw - yw) / torch.linalg.vector_norm(yw))
+    lin_all = max_over_ranks(lin_rank, dist, world)
+    del w, yw, Yw
 
     # ---- strong scaling: 1024 columns IN TOTAL, column-sharded (the BASELINE wording) -----------------------------------
     strong = None
@@ -696,7 +705,7 @@ def run_ours(args):
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "parity_rel_err_vs_oracle": parity,
         "parity": {"max_over_ranks_rel_err_vs_oracle": parity_all, "ranks_checked": world, "columns_per_rank": len(pcols),
-                   "tolerance": 1e-12},
+                   "full_batch_linearity_rel_err": lin_all, "full_batch_columns_per_rank": ncols, "tolerance": 1e-12},
         "strong_scaling": strong, "configs": configs,
     }
     print(json.dumps(line), flush=True)
