@@ -188,3 +188,32 @@ def test_comm_two_devices_single_process(tb):
     Y = np.concatenate([o.cpu().numpy() for o in outs], axis=1)
     assert rel(Y, ref) <= 1e-12
     comm.destroy()
+
+
+@pytest.mark.parametrize("n", [300, 5000, 70000])
+def test_unpaired_real_columns(tb, n):
+    """`pair_columns = 0`: every real column is transformed alone, as in the reference's column loop
+    (src/linearalgebra.jl:95-97) -- a NaN column or a column 1e100 times larger leaves its neighbours untouched.
+    With the default pairing the product is the same to 1e-12 on ordinary columns (checked here as well)."""
+    rng = np.random.default_rng(n)
+    vc, vr = 0.9 ** np.arange(n), 0.4 ** np.arange(n)
+    Ao = O.Toeplitz(vc, vr)
+    F = tb.factorize(tb.Toeplitz(torch.from_numpy(vc).cuda(), torch.from_numpy(vr).cuda()))
+    X = rng.standard_normal((n, 5))
+    Yo = np.stack([O.matvec(Ao, X[:, j]) for j in range(5)], axis=1)
+    Yp = tb.mul(F, devmat(X)).cpu().numpy()
+    tb.set_option("pair_columns", 0)
+    try:
+        Yu = tb.mul(F, devmat(X)).cpu().numpy()
+        assert rel(Yu, Yo) <= 1e-12 and rel(Yp, Yo) <= 1e-12
+        Xbad = X.copy()
+        Xbad[7, 0] = np.nan                      # partner of column 1 under pairing
+        Xbad[:, 2] *= 1e100                      # partner of column 3
+        Yb = tb.mul(F, devmat(Xbad)).cpu().numpy()
+        assert np.isnan(Yb[:, 0]).all() or np.isnan(Yb[:, 0]).any()
+        for j in (1, 3, 4):
+            assert np.isfinite(Yb[:, j]).all()
+            assert rel(Yb[:, j], Yo[:, j]) <= 1e-12
+        assert rel(Yb[:, 2], 1e100 * Yo[:, 2]) <= 1e-12
+    finally:
+        tb.set_option("pair_columns", 1)

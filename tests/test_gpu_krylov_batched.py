@@ -187,3 +187,33 @@ def test_batched_two_level_transforms_with_stragglers(tb, n, l):
     # single-vector solver == one-column batched solver
     x1, e1, i1, f1 = tb.cgs(Ad, torch.zeros(n, dtype=torch.float64, device="cuda"), _dev(B[:, 0].copy()), Md, 12, tol)
     assert i1 == its[0] and f1 == flags[0] and _rel(x1.cpu().numpy(), Xh[:, 0]) <= 1e-12
+
+
+@pytest.mark.parametrize("solver", ["cgs", "cg"])
+def test_nan_column_does_not_reach_its_pair(tb, solver):
+    """Real columns share complex transforms two by two; a column whose residual is NaN is frozen at once (with what
+    the reference's remaining iterations would report: iter = max_it, x all NaN, flag 1 for cgs, and 0 for cg whose
+    final `error > tol` is false for NaN, src/iterativeLinearSolvers.jl:95,205-213), so its partner's iterates are
+    those of the reference's independent column loop (src/linearalgebra.jl:102-110)."""
+    n, l = 3000, 4
+    rng = np.random.default_rng(5)
+    v = _p(0.5, n, np.float64)
+    Ao, Ad = O.SymmetricToeplitz(v), tb.SymmetricToeplitz(_dev(v))
+    Mo, Md = O.factorize(O.strang(Ao)), tb.factorize(tb.strang(Ad))
+    kA = PT.cond2(Ao.dense())
+    B = rng.standard_normal((n, l))
+    B[17, 0] = np.nan                            # column 0 pairs with column 1
+    tol = 100 * np.finfo(np.float64).eps
+    X = tb.colmajor(n, l, torch.float64)
+    X.zero_()
+    run = tb.cgs_batched if solver == "cgs" else tb.cg_batched
+    ref = O.cgs if solver == "cgs" else O.cg
+    X, errs, its, flags = run(Ad, X, _devmat(B), Md, 40, tol)
+    Xh = X.cpu().numpy()
+    assert np.isnan(Xh[:, 0]).all() and np.isnan(errs[0]) and its[0] == 40
+    assert flags[0] == (1 if solver == "cgs" else 0)
+    for j in range(1, l):
+        xo, eo, ito, fo = ref(Ao, np.zeros(n), B[:, j].copy(), Mo, 40, tol)
+        assert np.isfinite(Xh[:, j]).all()
+        assert flags[j] == fo and abs(its[j] - ito) <= 1
+        PT.check("%s batched beside a NaN column, col %d" % (solver, j), Xh[:, j], xo, np.float64, kA, extra=2.0 * kA * (eo + errs[j]))

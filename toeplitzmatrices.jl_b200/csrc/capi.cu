@@ -35,6 +35,7 @@ static std::atomic<int> g_time_passes{0};
 static std::atomic<int> g_ca_fuse{0};            // 1: pass C of a group + pass A of the next one on its stream as one launch; 2: + async x tile
 static std::atomic<int> g_pdl{1};                // programmatic dependent launch of passes B / C: 0 off, 1 products without group overlap, 2 always
 static std::atomic<int> g_l2_persist_mb{64};     // persisting-L2 carve-out for the two-level workspaces (0 = off); +4 % on config 2
+static std::atomic<int> g_pair_columns{1};       // real columns two per complex transform (0: one per transform, columns numerically independent)
 static std::atomic<int> g_tma{0};                // TMA-staged strided passes (tma_cols.cuh) where eligible; measured, see DESIGN.md
 extern int g_lev_gen;                            // levinson.cu
 int g_prune_half = 1;                            // pruned pass A / pass C when half of the embedding is padding
@@ -1042,6 +1043,7 @@ int tb200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "l2_persist_mb")) { g_l2_persist_mb = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 1024); return TB200_OK; }
     if (!strcmp(name, "lev_gen")) { g_lev_gen = (int)(value & 1); return TB200_OK; }
     if (!strcmp(name, "prune_half")) { g_prune_half = value ? 1 : 0; return TB200_OK; }
+    if (!strcmp(name, "pair_columns")) { g_pair_columns = value != 0; return TB200_OK; }
     if (!strcmp(name, "tma")) { g_tma = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 3); return TB200_OK; }   // bit 0: pass A loads, bit 1: pass C stores
     if (!strcmp(name, "overlap_streams")) { g_overlap_streams = (int)std::min<int64_t>(std::max<int64_t>(value, 0), tb200_fact::MAXS); return TB200_OK; }
     if (!strcmp(name, "l2max_f64")) { g_l2max_f64 = (int)value; return TB200_OK; }
@@ -1167,7 +1169,8 @@ static int mul_impl(tb200_fact* h, const void* spec, bool is_ldiv, void* y, int6
             return set_error(TB200_BAD_ARG, "a real y requires a real matrix, real x and real alpha/beta (InexactError in the reference)");
         if (is_ldiv && !h->a_real)
             return set_error(TB200_BAD_ARG, "real b with a complex Circulant (InexactError in the reference)");
-        c.x_mode = IO_PAIR; c.y_mode = IO_PAIR; c.nfft = (ncols + 1) / 2;
+        if (g_pair_columns.load()) { c.x_mode = IO_PAIR; c.y_mode = IO_PAIR; c.nfft = (ncols + 1) / 2; }
+        else { c.x_mode = IO_REAL; c.y_mode = IO_REAL; c.nfft = ncols; }
     } else {
         c.x_mode = mode_for(xc); c.y_mode = IO_CPLX; c.nfft = ncols;
     }
@@ -1704,6 +1707,13 @@ static int krylov_batched_t(bool is_cg, tb200_fact* A, tb200_fact* M, T* X, int6
         TB_KTRY(cuda_status(cudaGetLastError(), "batched Krylov kernels"));
         TB_KTRY(cuda_status(cudaMemcpyAsync(host_st.data(), st, sizeof(KState) * (size_t)c, cudaMemcpyDeviceToHost, s), "state readback"));
         TB_KTRY(cuda_status(cudaStreamSynchronize(s), "Krylov sync"));
+        bool any_nan = false;
+        for (int64_t j = 0; j < c; ++j) any_nan = any_nan || host_st[(size_t)j].pad != 0;
+        if (any_nan) {
+            k_bnanfill<T><<<dim3(gxe, (unsigned)c), 256, 0, s>>>(Xc, ldx, st, n);
+            count_launch();
+            TB_KTRY(cuda_status(cudaGetLastError(), "k_bnanfill"));
+        }
         for (int64_t j = 0; j < c; ++j) {
             if (err) err[c0 + j] = host_st[(size_t)j].error;
             if (iter) iter[c0 + j] = host_st[(size_t)j].iter;

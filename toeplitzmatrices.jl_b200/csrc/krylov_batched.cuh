@@ -85,7 +85,7 @@ __global__ void k_kstep(KState* __restrict__ st, int ncols, int step, int it, in
     case KS_BNRM:                                   // :136 / :44-47
         s.bnrm2 = sqrt(s.dot[0]);
         if (s.bnrm2 == 0.0) s.bnrm2 = 1.0;
-        s.iter = 0; s.flag = 0; s.active = 1;
+        s.iter = 0; s.flag = 0; s.active = 1; s.pad = 0;
         s.rho[0] = s.rho[1] = s.rho1[0] = s.rho1[1] = 0.0;
         break;
     case KS_INIT_CGS:                               // :152-156
@@ -93,6 +93,9 @@ __global__ void k_kstep(KState* __restrict__ st, int ncols, int step, int it, in
         s.error = sqrt(s.dot[0]) / s.bnrm2;
         if (s.error < tol) { s.active = 0; s.flag = (step == KS_INIT_CG) ? 2 : 0; }
         else if (max_it <= 0) { s.active = 0; s.flag = (step == KS_INIT_CG) ? 1 : -1; }    // empty loop: :205-213 with rho == 0 / :93-95
+        else if (s.error != s.error) {              // NaN right-hand side: frozen before it shares a transform (see KS_CGS_END)
+            s.active = 0; s.flag = (step == KS_INIT_CG) ? 0 : 1; s.pad = 1; s.iter = max_it;
+        }
         break;
     case KS_RHO0:
         s.rhon[0] = s.dot[0]; s.rhon[1] = s.dot[1];
@@ -117,6 +120,9 @@ __global__ void k_kstep(KState* __restrict__ st, int ncols, int step, int it, in
         s.error = sqrt(s.dot[0]) / s.bnrm2;
         s.rhon[0] = s.dot[2]; s.rhon[1] = s.dot[3];
         if (s.error <= tol) { s.active = 0; s.flag = 0; }
+        else if (s.error != s.error) {                      // NaN: the reference iterates on to max_it with NaN everywhere
+            s.active = 0; s.flag = 1; s.pad = (it < max_it); s.iter = max_it;   // (rho is NaN, not 0: flag 1); frozen here so that
+        }                                                   // the column leaves the pair it shares a transform with
         else {
             s.rho1[0] = s.rho[0]; s.rho1[1] = s.rho[1];
             if (it == max_it) { s.active = 0; s.flag = 1; }
@@ -133,6 +139,9 @@ __global__ void k_kstep(KState* __restrict__ st, int ncols, int step, int it, in
         if (!s.active) break;
         s.error = sqrt(s.dot[0]) / s.bnrm2;
         if (s.error <= tol) { s.active = 0; s.flag = 0; }
+        else if (s.error != s.error) {                      // NaN: as above; `error > tol` is false for NaN, so cg reports flag 0 (:95)
+            s.active = 0; s.flag = 0; s.pad = (it < max_it); s.iter = max_it;
+        }
         else {
             s.rho1[0] = s.rho[0]; s.rho1[1] = s.rho[1];
             if (it == max_it) { s.active = 0; s.flag = 1; }
@@ -225,6 +234,17 @@ __global__ void k_bx(T* __restrict__ x, long long ldx, const T* __restrict__ d, 
     const double2 alpha = make_double2(st[j].alpha[0], st[j].alpha[1]);
     const long long o = j * ld, ox = j * ldx;
     TB_KCOL_LOOP(n) { x[ox + i] = v_add(x[ox + i], s_mul<T>(alpha, d[o + i])); }
+}
+// columns frozen on a NaN residual before max_it: the reference's remaining iterations would have left x all NaN
+template <typename T>
+__global__ void k_bnanfill(T* __restrict__ x, long long ldx, const KState* __restrict__ st, long long n) {
+    const int j = blockIdx.y;
+    if (!st[j].pad) return;
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    const double2 nan2 = make_double2(qnan, qnan);
+    const long long ox = j * ldx;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        x[ox + i] = s_mul<T>(nan2, x[ox + i]);
 }
 // cg :69-76
 template <typename T>
