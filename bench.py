@@ -276,10 +276,34 @@ def run_configs(tb, rank, world, dist, peak, quick=False):
         for _ in range(3):
             tb.mul_(y, F, x); tb.mul_(y, A, x)
         t_mul = timed_region(lambda: tb.mul_(y, F, x), 200)
+        # the same call without the Python mirror's argument checks (what a `ccall` from the Julia extension pays), and as
+        # a captured CUDA graph (device time of the three dependent launches alone)
+        from toeplitz_b200 import _lib as L
+        from toeplitz_b200.api import _DT
+        lib, one, zero, dt = L.lib(), L.dbl2(1.0), L.dbl2(0.0), _DT[torch.float64]
+        xp, yp, st0 = x.data_ptr(), y.data_ptr(), torch.cuda.current_stream().cuda_stream
+        t_cabi = timed_region(lambda: lib.tb200_mul(F._h, yp, n, dt, xp, n, dt, 1, one, zero, st0), 200)
+        t_graph = None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                tb.mul_(y, F, x)
+                side.synchronize()
+                with torch.cuda.graph(graph, stream=side):
+                    tb.mul_(y, F, x)
+            graph.replay()
+            t_graph = timed_region(graph.replay, 200)
+        except Exception as e:                                   # a number, not a requirement of the bench
+            print("C1 graph replay skipped: %s" % str(e)[:120], file=sys.stderr)
         t_fac = timed_region(lambda: tb.factorize(A), 50)
         t_ref = timed_region(lambda: tb.mul_(y, A, x), 50)             # reference semantics: re-factorize on every call (:37)
         par = rel_err(y.cpu().numpy(), O.matvec(O.Toeplitz(vc, vr), xh))
         out["C1"] = {"workload": "Toeplitz{Float64} n=2^16, single vector (BASELINE configs[0])", "mul_us": t_mul * 1e6,
+                     "mul_us_c_abi": t_cabi * 1e6, "mul_us_graph_replay": None if t_graph is None else t_graph * 1e6,
+                     "note": "mul_us goes through the Python mirror of the reference API (host-bound: ~17 us of argument checks "
+                             "and launches per call); mul_us_c_abi is tb200_mul called directly",
                      "factorize_us": t_fac * 1e6, "mul_with_refactorize_us": t_ref * 1e6,
                      "roofline": {"bound": "latency (3 launches)", "achieved": 2 * n * 8 / t_mul / 1e9, "peak": peak, "unit": "GB/s",
                                   "frac": 2 * n * 8 / t_mul / 1e9 / peak, "alg_bytes_per_unit": 2 * n * 8},

@@ -23,6 +23,10 @@
  *    The reference's factorization cannot -- every product shares its single `tmp` vector
  *    (src/ToeplitzMatrices.jl:97-101).  A product on a stream other than the one that
  *    factorized waits for the spectrum by event; no host synchronisation is needed.
+ *  - CUDA graphs: after one warm-up call on the capturing stream (workspaces allocated, the
+ *    factorization seen complete) tb200_mul / tb200_circ_ldiv enqueue kernels and event
+ *    fork / joins only and can be captured; a capturing stream cannot wait for a factorization
+ *    still running on another stream (TB200_CUDA_ERR with a message saying so).
  *  - device memory comes from the stream-ordered pool; tb200_destroy orders the release
  *    after everything already queued on the streams that used the handle, so destroying
  *    right after an asynchronous call is safe.  The caller's vectors must outlive the

@@ -286,6 +286,7 @@ struct tb200_fact {
     // readiness of the spectrum / reciprocal spectrum: recorded on the stream that produced them; a product on any
     // OTHER stream waits for the event first (tb200_mul_host's internal streams included)
     cudaEvent_t ev_spec = nullptr, ev_inv = nullptr;
+    std::atomic<bool> spec_done{false}, inv_done{false};      // the event has been seen complete: no more waits
     cudaStream_t spec_stream = nullptr, inv_stream = nullptr;
     // Bluestein plan (Circulant, n not a power of two): spectrum kept in NATURAL order (n entries)
     bool bluestein = false;
@@ -495,14 +496,30 @@ static int ensure_buf(std::shared_ptr<DevBuf>& b, size_t bytes, const char* what
     return dev_alloc_on(b, bytes, what, s);
 }
 // a product on a stream other than the one that produced the spectrum waits for it
+// Once the event has been seen complete nothing is enqueued any more (and a stream under capture, which must not wait
+// on uncaptured work of another stream, can use the handle: warm up -- or synchronize -- before capturing).
+static int wait_ready(cudaEvent_t ev, std::atomic<bool>& done, cudaStream_t s, const char* what) {
+    if (done.load(std::memory_order_acquire)) return TB200_OK;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+    if (cs != cudaStreamCaptureStatusNone)
+        return set_error(TB200_CUDA_ERR, "%s: the factorization was produced on another stream and has not been seen complete; "
+                         "run one product (or synchronize) before capturing this stream", what);
+    const cudaError_t q = cudaEventQuery(ev);
+    if (q == cudaSuccess) { done.store(true, std::memory_order_release); return TB200_OK; }
+    if (q != cudaErrorNotReady) return cuda_status(q, what);
+    TB_CUDA(cudaStreamWaitEvent(s, ev, 0), what);
+    return TB200_OK;
+}
 static int wait_spectrum(tb200_fact* h, const void* spec, cudaStream_t s) {
-    if (h->ev_spec && s != h->spec_stream) TB_CUDA(cudaStreamWaitEvent(s, h->ev_spec, 0), "spectrum ready");
+    if (h->ev_spec && s != h->spec_stream) TB_TRY(wait_ready(h->ev_spec, h->spec_done, s, "spectrum ready"));
     if (spec && h->inv_spec && spec == h->inv_spec->p && h->ev_inv && s != h->inv_stream)
-        TB_CUDA(cudaStreamWaitEvent(s, h->ev_inv, 0), "reciprocal spectrum ready");
+        TB_TRY(wait_ready(h->ev_inv, h->inv_done, s, "reciprocal spectrum ready"));
     return TB200_OK;
 }
 static int mark_spectrum_ready(tb200_fact* h, cudaStream_t s) {
     if (!h->ev_spec) TB_CUDA(cudaEventCreateWithFlags(&h->ev_spec, cudaEventDisableTiming), "event");
+    h->spec_done.store(false);
     TB_CUDA(cudaEventRecord(h->ev_spec, s), "spectrum ready");
     h->spec_stream = s;
     h->spec_valid = true;
@@ -1310,6 +1327,7 @@ static int ensure_inv_spec(tb200_fact* h, cudaStream_t s) {
     TB_TRY(wait_spectrum(h, nullptr, s));
     TB_TRY(spec_map_launch(h, b->p, h->spec->p, OP_INV, 0.0, s));
     if (!h->ev_inv) TB_CUDA(cudaEventCreateWithFlags(&h->ev_inv, cudaEventDisableTiming), "event");
+    h->inv_done.store(false);
     TB_CUDA(cudaEventRecord(h->ev_inv, s), "reciprocal spectrum ready");
     h->inv_stream = s;
     h->inv_spec = b;
