@@ -302,8 +302,9 @@ def run_configs(tb, rank, world, dist, peak, quick=False):
         par = rel_err(y.cpu().numpy(), O.matvec(O.Toeplitz(vc, vr), xh))
         out["C1"] = {"workload": "Toeplitz{Float64} n=2^16, single vector (BASELINE configs[0])", "mul_us": t_mul * 1e6,
                      "mul_us_c_abi": t_cabi * 1e6, "mul_us_graph_replay": None if t_graph is None else t_graph * 1e6,
-                     "note": "mul_us goes through the Python mirror of the reference API (host-bound: ~17 us of argument checks "
-                             "and launches per call); mul_us_c_abi is tb200_mul called directly",
+                     "note": "mul_us goes through the Python mirror of the reference API (about 1 us of host time more than the "
+                             "device needs per call); mul_us_c_abi is tb200_mul called directly, mul_us_graph_replay the device "
+                             "time of the three dependent launches",
                      "factorize_us": t_fac * 1e6, "mul_with_refactorize_us": t_ref * 1e6,
                      "roofline": {"bound": "latency (3 launches)", "achieved": 2 * n * 8 / t_mul / 1e9, "peak": peak, "unit": "GB/s",
                                   "frac": 2 * n * 8 / t_mul / 1e9 / peak, "alg_bytes_per_unit": 2 * n * 8},
