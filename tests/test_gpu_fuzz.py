@@ -5,6 +5,8 @@ regimes than the FFTW path has (direct product for N < 512, one shared-memory tr
 transform, chirp-z for non-power-of-two circulants, two real columns packed per transform, odd column
 tails, padded leading dimensions, alpha/beta epilogue), so this sweep draws sizes log-uniformly across
 all of them.  Tolerances: relative 2-norm error 1e-12 (Float64 family) / 1e-5 (Float32 family)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -13,6 +15,15 @@ from oracle import toeplitz_oracle as O
 import parity_tools as PT
 
 pytestmark = pytest.mark.gpu
+
+# soak runs: TB200_FUZZ_SCALE=8 multiplies the number of seeds, TB200_FUZZ_SEED0 shifts them (defaults: the committed sweep)
+_SCALE = max(1, int(os.environ.get("TB200_FUZZ_SCALE", "1")))
+_SEED0 = int(os.environ.get("TB200_FUZZ_SEED0", "0"))
+
+
+def _seeds(k):
+    return range(_SEED0, _SEED0 + k * _SCALE)
+
 
 KINDS = ["toeplitz", "symmetric", "circulant", "lower", "upper", "hankel"]
 DTYPES = [np.float64, np.complex128, np.float32, np.complex64]
@@ -49,6 +60,19 @@ def _rel(a, b):
     return np.linalg.norm((a - b).ravel()) / (den if den > 0 else 1.0)
 
 
+def _amp(Ao, m, n, X, Y):
+    """An output of few rows can come out small by chance (m = 1 is a single dot product of n terms): the rounding
+    error of the FFT product -- reference and CUDA path alike -- is relative to the circular convolution the rows are
+    cut from, about ||coefficients|| * ||x|| * sqrt(m / N) for these random inputs, not to ||y|| itself.  Returns the
+    ratio (>= 1) that widens the relative tolerance in those cases; ~1 for ordinary shapes."""
+    if hasattr(Ao, "vc"):
+        cn = np.sqrt(np.linalg.norm(Ao.vc) ** 2 + np.linalg.norm(Ao.vr) ** 2)
+    else:
+        cn = np.linalg.norm(Ao.v)
+    expected = float(cn) * float(np.linalg.norm(X)) * np.sqrt(m / float(m + n - 1))
+    return max(1.0, expected / max(float(np.linalg.norm(Y)), 1e-300))
+
+
 def _size(rng, hi):
     return int(np.exp(rng.uniform(0.0, np.log(hi))))
 
@@ -70,7 +94,7 @@ def _build(tb, rng, kind, dtype, hi):
     return getattr(O, cls)(v), getattr(tb, cls)(_dev(v)), n, n
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", _seeds(12))
 def test_mul_random_shapes(tb, seed):
     rng = np.random.default_rng(1000 + seed)
     for case in range(14):
@@ -90,10 +114,12 @@ def test_mul_random_shapes(tb, seed):
         want = O.matvec(Ao, X)
         # plain product, padded leading dimension on the input
         got = tb.mul(Ad, _devmat_padded(X, int(rng.integers(0, 9)))).cpu().numpy()
-        assert _rel(got, want) <= tol, tag
+        amp = _amp(Ao, m, n, X, want)
+        assert _rel(got, want) <= tol * amp, tag + " (amp %.2f)" % amp
         # vector form (takes the direct product when m + n - 1 < 512, src/linearalgebra.jl:19-34)
         gv = tb.mul(Ad, _dev(X[:, 0].copy())).cpu().numpy()
-        assert _rel(gv, want[:, 0]) <= tol, tag + " (vector)"
+        amp0 = _amp(Ao, m, n, X[:, 0], want[:, 0])
+        assert _rel(gv, want[:, 0]) <= tol * amp0, tag + " (vector, amp %.2f)" % amp0
         # alpha / beta epilogue into a padded y through a factorization (src/linearalgebra.jl:42-80)
         ydt = want.dtype
         alpha = float(rng.standard_normal())
@@ -105,13 +131,13 @@ def test_mul_random_shapes(tb, seed):
         ref = alpha * want + beta * Y0
         # alpha*A*x + beta*y can cancel: the error is relative to the two terms, not to their sum
         cancel = (abs(alpha) * np.linalg.norm(want) + abs(beta) * np.linalg.norm(Y0)) / max(np.linalg.norm(ref), 1e-300)
-        assert _rel(Yd.cpu().numpy(), ref) <= tol * max(1.0, cancel), tag + " (alpha, beta; cancellation %.2f)" % cancel
+        assert _rel(Yd.cpu().numpy(), ref) <= tol * max(1.0, cancel) * amp, tag + " (alpha, beta; cancellation %.2f)" % cancel
         # the padding rows of y were not touched
         base = Yd._base if Yd._base is not None else Yd
         assert bool(torch.isnan(torch.view_as_real(base) if base.is_complex() else base).any()) == (Yd.stride(1) > m), tag
 
 
-@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("seed", _seeds(4))
 def test_circulant_solves_random_sizes(tb, seed):
     """ldiv!/inv/eigvals of Circulant (src/linearalgebra.jl:225-253,286-287) at random sizes: power-of-two plans
     (one-level and two-level) and chirp-z plans."""
@@ -138,7 +164,7 @@ def test_circulant_solves_random_sizes(tb, seed):
         PT.check(tag + " inv", tb.inv(Cd).vc.cpu().numpy(), O.circ_inv(Co).vc, dtype, kC)
 
 
-@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("seed", _seeds(4))
 def test_levinson_durbin_random_sizes(tb, seed):
     """Batched levinson!/durbin! (src/directLinearSolvers.jl:15-28,100-134) at random orders and batch sizes,
     warp kernel (n <= 512) and block kernel (n > 512), against the C oracle."""
