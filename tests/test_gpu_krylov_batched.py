@@ -217,3 +217,76 @@ def test_nan_column_does_not_reach_its_pair(tb, solver):
         assert np.isfinite(Xh[:, j]).all()
         assert flags[j] == fo and abs(its[j] - ito) <= 1
         PT.check("%s batched beside a NaN column, col %d" % (solver, j), Xh[:, j], xo, np.float64, kA, extra=2.0 * kA * (eo + errs[j]))
+
+
+import os
+
+_KSCALE = max(1, int(os.environ.get("TB200_FUZZ_SCALE", "1")))
+_KSEED0 = int(os.environ.get("TB200_FUZZ_SEED0", "0"))
+
+
+@pytest.mark.parametrize("seed", range(_KSEED0, _KSEED0 + 6 * _KSCALE))
+def test_batched_krylov_random_batches(tb, seed):
+    """Seeded sweep of the batched drivers against the oracle's column loop: random order (one shared-memory transform
+    or the two-level path, forced into several column groups), column count, element type, preconditioner (Strang /
+    T. Chan), chunking of the work vectors, and a random mix of column kinds -- zero columns (early return),
+    a column solved at once, columns 1e6 times larger or smaller than their pair partner, ordinary ones -- so that columns
+    leave the active set at different iterations.  Per column: same flag, iteration count within one, solution within
+    cond * (both residuals)."""
+    rng = np.random.default_rng(7000 + seed)
+    n = int(np.exp(rng.uniform(np.log(300), np.log(30000))))
+    l = int(rng.integers(1, 11))
+    use_cg = rng.random() < 0.35
+    dtype = np.float64 if use_cg else [np.float64, np.complex128, np.complex64][int(rng.integers(3))]
+    single = np.dtype(dtype) == np.dtype(np.complex64)
+    rho = float(rng.uniform(0.2, 0.7))
+    v = _p(rho, n, dtype)
+    Ao, Ad = O.SymmetricToeplitz(v), tb.SymmetricToeplitz(_dev(v))
+    kA = ((1.0 + rho) / (1.0 - rho)) ** 2          # KMS symbol (1 - rho^2) / |1 - rho z|^2: max / min on the unit circle
+    pc = ["strang", "chan"][int(rng.integers(2))]
+    Mo = O.factorize(getattr(O, pc)(Ao))
+    Md = tb.factorize(getattr(tb, pc)(Ad))
+    B = rng.standard_normal((n, l)).astype(dtype)
+    if np.dtype(dtype).kind == "c":
+        B = (B + 1j * rng.standard_normal((n, l))).astype(dtype)
+    kinds = []
+    e0 = np.zeros(n, dtype); e0[0] = 1
+    for j in range(l):
+        k = int(rng.integers(6))
+        kinds.append(k)
+        if k == 0:
+            B[:, j] = 0
+        elif k == 1:
+            B[:, j] = O.matvec(Ao, e0)
+        elif k == 2:
+            B[:, j] *= 1e6
+        elif k == 3:
+            B[:, j] *= 1e-6
+    tol = 2e-5 if single else 1e-13
+    max_it = int(rng.integers(3, 40))
+    tb.set_option("group_bytes", 1 << 20)
+    tb.set_option("krylov_work_bytes", int(rng.choice([16 << 30, 8 * n * np.dtype(dtype).itemsize * 3, 8 * n * np.dtype(dtype).itemsize * 5])))
+    try:
+        X = tb.colmajor(n, l, _dev(B[:1]).dtype)
+        X.zero_()
+        run = tb.cg_batched if use_cg else tb.cgs_batched
+        X, errs, its, flags = run(Ad, X, _devmat(B), Md, max_it, tol)
+    finally:
+        tb.set_option("group_bytes", 48 << 20)
+        tb.set_option("krylov_work_bytes", 16 << 30)
+    Xh = X.cpu().numpy()
+    tag = "seed %d: %s n=%d l=%d %s pc=%s max_it=%d kinds=%s" % (seed, "cg" if use_cg else "cgs", n, l, np.dtype(dtype).name, pc,
+                                                              max_it, kinds)
+    for j in range(l):
+        res = (O.cg if use_cg else O.cgs)(Ao, np.zeros(n, dtype), B[:, j].copy(), Mo, max_it, tol)
+        if res is None:
+            assert flags[j] == 2 and its[j] == 0, tag
+            continue
+        xo, eo, ito, fo = res
+        near_tol = min(eo, errs[j]) <= 4 * tol and max(eo, errs[j]) >= tol / 4      # stopped on different sides of tol
+        assert abs(its[j] - ito) <= 1, (tag, j, its[j], ito)
+        assert flags[j] == fo or near_tol, (tag, j, flags[j], fo, errs[j], eo)
+        if np.linalg.norm(xo) > 0:
+            PT.check("krylov fuzz %s col %d" % (tag, j), Xh[:, j], xo, dtype, kA, extra=2.0 * kA * (eo + errs[j]))
+        else:
+            assert np.linalg.norm(Xh[:, j]) == 0, tag

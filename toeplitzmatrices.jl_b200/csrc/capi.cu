@@ -11,6 +11,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include <cuda.h>
@@ -1651,16 +1652,23 @@ static int krylov_batched_t(bool is_cg, tb200_fact* A, tb200_fact* M, T* X, int6
             sel.colmap = cm;
             return mul_impl(M, M->inv_spec->p, true, out_v, n, dtype, in_v, n, dtype, cm ? ncol : c, one, zero, s, &sel);
         };
+        // x_j and r_j = b_j enter the iteration scaled by the column's power of two (k_kstep KS_BNRM)
+        auto scaled_start = [&](T* r) -> int {
+            k_bscale<T><<<dim3(gxe, (unsigned)c), 256, 0, s>>>(Xc, ldx, st, n, 0);
+            count_launch();
+            k_bcopy_scaled<T><<<dim3(gxe, (unsigned)c), 256, 0, s>>>(r, n, Bc, ldb, st, n);
+            count_launch();
+            return cuda_status(cudaGetLastError(), "k_bcopy_scaled");
+        };
         // small problems are launch-bound: read the live count every third iteration only (stale counts are safe, see k_compact)
         auto sync_now = [&](int it) { return (long long)n * std::max(h_active, 1) >= (1ll << 19) || it % 3 == 0 || it == max_it; };
         TB_KTRY(cuda_status(cudaMemsetAsync(counters->p, 0, sizeof(unsigned) * (size_t)c, s), "memset"));
         TB_KTRY(cuda_status(cudaMemsetAsync(work->p, 0, sizeof(T) * vsz * nvec, s), "memset"));          // :141-146 zeros
         TB_KTRY(dots(Bc, Bc, ldb, nullptr, nullptr, 0, (int)c));
-        TB_KTRY(step(KS_BNRM, 0));
+        TB_KTRY(step(KS_BNRM, (std::is_same<T, float>::value || std::is_same<T, float2>::value) ? 100 : 900));
         if (!is_cg) {
             T* u = w; T* p = u + vsz; T* ph = p + vsz; T* q = ph + vsz; T* uh = q + vsz; T* vh = uh + vsz; T* r = vh + vsz; T* rt = r + vsz;
-            TB_KTRY(cuda_status(cudaMemcpy2DAsync(r, sizeof(T) * (size_t)n, Bc, sizeof(T) * (size_t)ldb, sizeof(T) * (size_t)n, (size_t)c,
-                                                  cudaMemcpyDeviceToDevice, s), "copy"));                   // :149
+            TB_KTRY(scaled_start(r));                                                                       // :149 (in units of ~||b_j||)
             TB_KTRY(mulA(r, Xc, ldx, c, minus, one, true, false));                                          // :150
             TB_KTRY(dots(r, r, n, nullptr, nullptr, 0, (int)c));
             TB_KTRY(step(KS_INIT_CGS, 0));
@@ -1698,8 +1706,7 @@ static int krylov_batched_t(bool is_cg, tb200_fact* A, tb200_fact* M, T* X, int6
             }
         } else {
             T* z = w; T* q = z + vsz; T* p = q + vsz; T* r = p + vsz;
-            TB_KTRY(cuda_status(cudaMemcpy2DAsync(r, sizeof(T) * (size_t)n, Bc, sizeof(T) * (size_t)ldb, sizeof(T) * (size_t)n, (size_t)c,
-                                                  cudaMemcpyDeviceToDevice, s), "copy"));
+            TB_KTRY(scaled_start(r));
             TB_KTRY(mulA(r, Xc, ldx, c, minus, one, true, false));                                          // :55
             TB_KTRY(dots(r, r, n, nullptr, nullptr, 0, (int)c));
             TB_KTRY(step(KS_INIT_CG, 0));
@@ -1723,6 +1730,8 @@ static int krylov_batched_t(bool is_cg, tb200_fact* A, tb200_fact* M, T* X, int6
             }
         }
         TB_KTRY(cuda_status(cudaGetLastError(), "batched Krylov kernels"));
+        k_bscale<T><<<dim3(gxe, (unsigned)c), 256, 0, s>>>(Xc, ldx, st, n, 1);                             // back to the units of b_j
+        count_launch();
         TB_KTRY(cuda_status(cudaMemcpyAsync(host_st.data(), st, sizeof(KState) * (size_t)c, cudaMemcpyDeviceToHost, s), "state readback"));
         TB_KTRY(cuda_status(cudaStreamSynchronize(s), "Krylov sync"));
         bool any_nan = false;

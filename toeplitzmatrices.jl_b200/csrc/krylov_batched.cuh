@@ -17,6 +17,7 @@ namespace tb {
 struct KState {
     double rho[2], rho1[2], rhon[2], alpha[2], beta[2], dot[4];
     double bnrm2, error;
+    double scale, iscale;          // power of two that brings ||b_j|| into [0.5, 1), and its inverse (see KS_BNRM)
     int iter, flag, active, pad;
 };
 
@@ -85,6 +86,20 @@ __global__ void k_kstep(KState* __restrict__ st, int ncols, int step, int it, in
     case KS_BNRM:                                   // :136 / :44-47
         s.bnrm2 = sqrt(s.dot[0]);
         if (s.bnrm2 == 0.0) s.bnrm2 = 1.0;
+        // Every column iterates in units of a power of two near its own ||b||: real columns share complex transforms two
+        // by two, and a product's rounding error is relative to the larger column of a pair, so a right-hand side 10^k
+        // times smaller than its partner would stall k digits above the tolerance.  Scaling by a power of two is exact:
+        // the iterates are those of the unscaled column, bit for bit, and x is scaled back at the end.
+        s.scale = 1.0; s.iscale = 1.0;
+        if (s.bnrm2 > 0.0 && s.bnrm2 < 1.0e300) {
+            int e = 0;
+            frexp(s.bnrm2, &e);
+            const int emax = it > 0 ? it : 900;          // KS_BNRM: `it` carries the exponent range of the vectors' precision
+            e = e < -emax ? -emax : (e > emax ? emax : e);
+            s.scale = ldexp(1.0, -e);
+            s.iscale = ldexp(1.0, e);
+            s.bnrm2 *= s.scale;
+        }
         s.iter = 0; s.flag = 0; s.active = 1; s.pad = 0;
         s.rho[0] = s.rho[1] = s.rho1[0] = s.rho1[1] = 0.0;
         break;
@@ -234,6 +249,27 @@ __global__ void k_bx(T* __restrict__ x, long long ldx, const T* __restrict__ d, 
     const double2 alpha = make_double2(st[j].alpha[0], st[j].alpha[1]);
     const long long o = j * ld, ox = j * ldx;
     TB_KCOL_LOOP(n) { x[ox + i] = v_add(x[ox + i], s_mul<T>(alpha, d[o + i])); }
+}
+// x_j *= scale_j (dir = 0, before the first residual) or iscale_j (dir = 1, at the end); every column, frozen or not
+template <typename T>
+__global__ void k_bscale(T* __restrict__ x, long long ldx, const KState* __restrict__ st, long long n, int dir) {
+    const int j = blockIdx.y;
+    const double f = dir ? st[j].iscale : st[j].scale;
+    if (f == 1.0) return;
+    const double2 f2 = make_double2(f, 0.0);
+    const long long ox = j * ldx;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        x[ox + i] = s_mul<T>(f2, x[ox + i]);
+}
+// r_j = scale_j * b_j
+template <typename T>
+__global__ void k_bcopy_scaled(T* __restrict__ r, long long ld, const T* __restrict__ b, long long ldb, const KState* __restrict__ st,
+                               long long n) {
+    const int j = blockIdx.y;
+    const double2 f2 = make_double2(st[j].scale, 0.0);
+    const long long o = j * ld, ob = j * ldb;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        r[o + i] = s_mul<T>(f2, b[ob + i]);
 }
 // columns frozen on a NaN residual before max_it: the reference's remaining iterations would have left x all NaN
 template <typename T>
