@@ -187,3 +187,92 @@ def test_levinson_durbin_random_sizes(tb, seed):
             Xm = tb.levinson(tb.SymmetricToeplitz(_dev(vc)), _devmat_padded(Bm, 0)).cpu().numpy()
             Rrep = np.asfortranarray(np.repeat(Rl[:, :1], nsys, axis=1))
             assert _rel(Xm, OC.c_levinson_batched(Rrep, Bm) / 1.7) <= 1e-12, tag + " (multi-rhs)"
+
+
+@pytest.mark.parametrize("seed", _seeds(3))
+def test_mul_host_random_shapes(tb, seed):
+    """`tb200_mul_host` (host matrices in, host matrices out through the three-slot copy / compute / copy pipeline) at
+    random shapes: pinned or pageable memory, padded leading dimensions, odd column counts, chunk sizes that cut the
+    columns into one to many chunks, alpha / beta, all four element types."""
+    rng = np.random.default_rng(4000 + seed)
+    for case in range(6):
+        kind = ["toeplitz", "symmetric", "hankel", "lower"][int(rng.integers(4))]
+        dtype = DTYPES[int(rng.integers(len(DTYPES)))]
+        single = np.dtype(dtype) in (np.dtype(np.float32), np.dtype(np.complex64))
+        Ao, Ad, m, n = _build(tb, rng, kind, dtype, 30000 if case % 3 == 0 else 4000)
+        ncols = int(rng.integers(1, 24))
+        padx, pady = int(rng.integers(0, 7)), int(rng.integers(0, 7))
+        X = _rand(rng, (n, ncols), dtype)
+        Y0 = _rand(rng, (m, ncols), dtype)
+        tdt = torch.from_numpy(X[:0]).dtype
+        Xb = torch.zeros((ncols, n + padx), dtype=tdt)
+        Yb = torch.full((ncols, m + pady), float("nan"), dtype=tdt)
+        if rng.random() < 0.5:
+            Xb, Yb = Xb.pin_memory(), Yb.pin_memory()
+        Xb[:, :n] = torch.from_numpy(np.ascontiguousarray(X.T))
+        Yb[:, :m] = torch.from_numpy(np.ascontiguousarray(Y0.T))
+        Xh, Yh = Xb.t()[:n, :], Yb.t()[:m, :]
+        with_beta = rng.random() < 0.5
+        alpha = float(rng.standard_normal()) if with_beta else 1.0
+        beta = float(rng.standard_normal()) if with_beta else 0.0
+        col_bytes = max(n, m) * np.dtype(dtype).itemsize
+        chunk = int(rng.choice([1 << 20, 3 * col_bytes, 8 * col_bytes, 256 << 20]))
+        tag = "host seed %d case %d: %s %s m=%d n=%d cols=%d pad=(%d,%d) chunk=%d beta=%s" % (
+            seed, case, kind, np.dtype(dtype).name, m, n, ncols, padx, pady, chunk, with_beta)
+        F = tb.factorize(Ad)
+        tb.set_option("host_chunk_bytes", chunk)
+        try:
+            tb.mul_host_(Yh, F, Xh, alpha, beta)
+        finally:
+            tb.set_option("host_chunk_bytes", 256 << 20)
+        want = O.matvec(Ao, X)
+        ref = alpha * want + beta * Y0
+        tol = 1e-5 if single else 1e-12
+        cancel = (abs(alpha) * np.linalg.norm(want) + abs(beta) * np.linalg.norm(Y0)) / max(np.linalg.norm(ref), 1e-300)
+        amp = _amp(Ao, m, n, X, want)
+        assert _rel(Yh.numpy(), ref) <= tol * max(1.0, cancel) * amp, tag
+        if pady:
+            assert bool(torch.isnan(Yb[:, m:]).all()), tag + " (padding)"
+
+
+@pytest.mark.parametrize("seed", _seeds(3))
+def test_circulant_algebra_and_triangular_inverse_random_sizes(tb, seed):
+    """pinv / sqrt / C1*C2 of Circulants (src/linearalgebra.jl:194-222,276-284,311-315) and inv of triangular Toeplitz
+    matrices by recursive doubling (:337-396) at random sizes (power-of-two and chirp-z plans; every doubling depth)."""
+    rng = np.random.default_rng(5000 + seed)
+    for case in range(6):
+        dtype = [np.float64, np.complex128, np.complex64][int(rng.integers(3))]
+        n = max(2, _size(rng, 20000))
+        if case % 3 == 0:
+            n = 1 << int(rng.integers(1, 15))
+        v = _rand(rng, n, dtype)
+        v[0] += 4.0 * np.sqrt(n)
+        w = _rand(rng, n, dtype)
+        Co, Cd = O.Circulant(v), tb.Circulant(_dev(v))
+        Wo, Wd = O.Circulant(w), tb.Circulant(_dev(w))
+        tag = "fuzz circulant algebra seed %d case %d: %s n=%d" % (seed, case, np.dtype(dtype).name, n)
+        kC = PT.cond_spectrum(np.fft.fft(v.astype(np.complex128)))
+        PT.check(tag + " pinv", tb.pinv(Cd).vc.cpu().numpy(), O.circ_pinv(Co).vc, dtype, kC)
+        PT.check(tag + " C*W", tb.circ_mul(Cd, Wd).vc.cpu().numpy(), O.circ_mul(O.factorize(Co), O.factorize(Wo)).vc, dtype)
+        if np.dtype(dtype).kind == "c":              # sqrt of a real Circulant with negative eigenvalues is an InexactError (:311-315)
+            # square roots of eigenvalues next to the branch cut differ by sign between two roundings of the same
+            # spectrum: compare the squares (sqrt(C)^2 == C), as the reference's own test does (test/runtests.jl:573-576)
+            S = tb.sqrt(Cd)
+            PT.check(tag + " sqrt(C)^2", tb.circ_mul(S, S).vc.cpu().numpy(), v, dtype, np.sqrt(kC))
+    for case in range(4):
+        dtype = [np.float64, np.complex128][int(rng.integers(2))]
+        n = max(1, _size(rng, 6000))
+        r = float(rng.uniform(0.3, 0.8))
+        v = np.concatenate([[1.0], 0.5 * r ** np.arange(1, n)]).astype(dtype)
+        if np.dtype(dtype).kind == "c":
+            v = v * np.exp(0.3j * np.arange(n))
+        # symbol 1 + 0.5 z / (1 - r z) on |z| = 1 bounds the condition number of every leading block
+        z = np.exp(2j * np.pi * np.arange(2048) / 2048)
+        f = 1.0 + 0.5 * z / (1.0 - r * z)
+        kL = float(np.abs(f).max() / np.abs(f).min())
+        tag = "fuzz tri inv seed %d case %d: %s n=%d r=%.2f" % (seed, case, np.dtype(dtype).name, n, r)
+        got = tb.inv(tb.LowerTriangularToeplitz(_dev(v))).v.cpu().numpy()
+        PT.check(tag, got, O.tri_inv_lower(v), dtype, kL)
+        # the definition: L(v) * L(inv) = I, checked on the first column through the oracle's own product
+        e0 = np.zeros(n, dtype); e0[0] = 1
+        PT.check(tag + " L*inv(L) e0", O.matvec(O.LowerTriangularToeplitz(v), got), e0, dtype, kL)
