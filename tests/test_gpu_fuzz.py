@@ -167,12 +167,14 @@ def test_circulant_solves_random_sizes(tb, seed):
 @pytest.mark.parametrize("seed", _seeds(4))
 def test_levinson_durbin_random_sizes(tb, seed):
     """Batched levinson!/durbin! (src/directLinearSolvers.jl:15-28,100-134) at random orders and batch sizes,
-    warp kernel (n <= 512) and block kernel (n > 512), against the C oracle."""
+    one warp or lane group per system (n <= 512), two / four warps (n <= 2048), one CTA per system in shared memory or
+    in an L2-resident workspace (beyond), against the C oracle."""
     from oracle import build_oracle as OC
     rng = np.random.default_rng(3000 + seed)
     for case in range(8):
-        n = max(2, _size(rng, 1500))
-        nsys = int(rng.integers(1, 70))
+        big = case == 7                             # one order per seed beyond the register kernels (one CTA per system)
+        n = int(rng.integers(2049, 9000)) if big else max(2, _size(rng, 2048))
+        nsys = int(rng.integers(1, 12 if big else 70))
         R = np.asfortranarray(rng.random((n, nsys)) / n)
         Bm = np.asfortranarray(rng.standard_normal((n, nsys)))
         tag = "seed %d case %d: n=%d nsys=%d" % (seed, case, n, nsys)
