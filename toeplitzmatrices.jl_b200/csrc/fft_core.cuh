@@ -95,9 +95,92 @@ __device__ __forceinline__ cx<R> mul_w16(cx<R> d, int k) {
     }
 }
 
+// ---- fused-multiply-add butterflies (TB_FMA_BFLY) -------------------------------------------------------------
+// u' = u + w v, v' = u - w v with w = exp(-/+ 2 pi i k/16): the twiddle rides the additions.  General w: the sum in four
+// FMAs and the difference as 2u - (u + w v) in two more (six instructions instead of 4 + 4); w = (+-1 +- i)/sqrt(2): two
+// additions and four FMAs (instead of 2 + 2 + 4).  Both register transforms use the decimation-in-time order (bit-
+// reversed in, natural out) so that every twiddle sits in front of a butterfly; the forward transform's natural-in /
+// bit-reversed-out contract is kept by renaming registers, which costs nothing once the loops are unrolled.
+#ifndef TB_FMA_BFLY
+#define TB_FMA_BFLY 1
+#endif
+template <typename R, bool INV>
+__device__ __forceinline__ void bfly_w16(cx<R>& u, cx<R>& v, int k) {
+    const R C1 = (R)0.92387953251128675613, S1 = (R)0.38268343236508977173;
+    const R C2 = (R)0.70710678118654752440;
+    switch (k) {
+    case 0: { const cx<R> s = cadd(u, v); v = csub(u, v); u = s; return; }
+    case 4: {
+        const cx<R> t = INV ? mk<R>(-v.y, v.x) : mk<R>(v.y, -v.x);
+        const cx<R> s = cadd(u, t); v = csub(u, t); u = s; return;
+    }
+    case 2: case 6: {
+        // w v = C2 * (p, q):  k = 2: fwd (vx + vy, vy - vx), inv (vx - vy, vx + vy);  k = 6: fwd (vy - vx, -(vx + vy)), inv (-(vx + vy), vx - vy)
+        const R sum = v.x + v.y, dif = v.x - v.y;
+        R pp, qq;
+        if (k == 2) { pp = INV ? dif : sum; qq = INV ? sum : -dif; }
+        else        { pp = INV ? -sum : -dif; qq = INV ? dif : -sum; }
+        const cx<R> s = mk<R>(fma(C2, pp, u.x), fma(C2, qq, u.y));
+        v = mk<R>(fma(-C2, pp, u.x), fma(-C2, qq, u.y));
+        u = s;
+        return;
+    }
+    default: {
+        const R wr = (k == 1) ? C1 : (k == 3) ? S1 : (k == 5) ? -S1 : -C1;
+        const R ws = (k == 1 || k == 7) ? S1 : C1;
+        const R wi = INV ? ws : -ws;
+        const cx<R> s = mk<R>(fma(v.x, wr, fma(-v.y, wi, u.x)), fma(v.x, wi, fma(v.y, wr, u.y)));
+        v = mk<R>(fma((R)2, u.x, -s.x), fma((R)2, u.y, -s.y));
+        u = s;
+        return;
+    }
+    }
+}
+// a[brev(c)] = x[c] in -> natural out; INV selects the conjugate twiddles
+template <typename R, int RAD, bool INV, int H0 = 1>
+__device__ __forceinline__ void dit_fused(cx<R>* a) {
+#pragma unroll
+    for (int h = H0; h <= RAD / 2; h <<= 1) {
+#pragma unroll
+        for (int blk = 0; blk < RAD; blk += 2 * h) {
+#pragma unroll
+            for (int i = 0; i < h; ++i) bfly_w16<R, INV>(a[blk + i], a[blk + i + h], i * (8 / h));
+        }
+    }
+}
+
+// Inverse stage with its twiddles: element c (held in a[brev(c)]) is multiplied by conj(w[c]), c >= 1, and the first
+// decimation-in-time level pairs elements c and c + RAD/2 -- one product, then the sum in four FMAs and the difference
+// as 2p - s (ten instructions per pair instead of twelve).
+template <typename R, int RAD>
+__device__ __forceinline__ void dit_regs_tw(cx<R>* a, const cx<R>* w) {
+    constexpr int LG = ilog2c(RAD);
+#pragma unroll
+    for (int m = 0; m < RAD / 2; ++m) {
+        const int c0 = brev(2 * m, LG), c1 = brev(2 * m + 1, LG);
+        const cx<R> p = (c0 == 0) ? a[2 * m] : cmulc(a[2 * m], w[c0]);
+        const cx<R> v = a[2 * m + 1], ww = w[c1];
+        const cx<R> sum = mk<R>(fma(v.x, ww.x, fma(v.y, ww.y, p.x)), fma(v.y, ww.x, fma(-v.x, ww.y, p.y)));
+        a[2 * m + 1] = mk<R>(fma((R)2, p.x, -sum.x), fma((R)2, p.y, -sum.y));
+        a[2 * m] = sum;
+    }
+    dit_fused<R, RAD, true, 2>(a);
+}
+
 // In-register radix-RAD DIF butterfly: natural in -> a[brev(c)] = X[c].
 template <typename R, int RAD>
 __device__ __forceinline__ void dif_regs(cx<R>* a) {
+#if TB_FMA_BFLY
+    {
+        cx<R> b[RAD];
+#pragma unroll
+        for (int i = 0; i < RAD; ++i) b[brev(i, ilog2c(RAD))] = a[i];
+        dit_fused<R, RAD, false>(b);
+#pragma unroll
+        for (int c = 0; c < RAD; ++c) a[brev(c, ilog2c(RAD))] = b[c];
+        return;
+    }
+#endif
 #pragma unroll
     for (int h = RAD / 2; h >= 1; h >>= 1) {
 #pragma unroll
@@ -116,6 +199,18 @@ __device__ __forceinline__ void dif_regs(cx<R>* a) {
 template <typename R, int RAD>
 __device__ __forceinline__ void dif_regs_halfzero(cx<R>* a) {
     static_assert(RAD == 16, "half-zero variant is written for radix-16 threads");
+#if TB_FMA_BFLY
+    {
+        // bit-reversed order puts the zero half on the odd positions: the first decimation-in-time level is a copy
+        cx<R> b[RAD];
+#pragma unroll
+        for (int i = 0; i < RAD / 2; ++i) { b[brev(i, 4)] = a[i]; b[brev(i, 4) + 1] = a[i]; }
+        dit_fused<R, RAD, false, 2>(b);
+#pragma unroll
+        for (int c = 0; c < RAD; ++c) a[brev(c, 4)] = b[c];
+        return;
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < RAD / 2; ++i) a[i + RAD / 2] = mul_w16<R, false>(a[i], i);
 #pragma unroll
@@ -134,6 +229,10 @@ __device__ __forceinline__ void dif_regs_halfzero(cx<R>* a) {
 // Mirror: a[brev(c)] = X[c] in -> natural out, conjugate twiddles (unnormalised inverse).
 template <typename R, int RAD>
 __device__ __forceinline__ void dit_regs(cx<R>* a) {
+#if TB_FMA_BFLY
+    dit_fused<R, RAD, true>(a);
+    return;
+#endif
 #pragma unroll
     for (int h = 1; h <= RAD / 2; h <<= 1) {
 #pragma unroll
@@ -357,13 +456,19 @@ struct SlotFFT {
 #pragma unroll
                 for (int c = 0; c < E; ++c) TB_SM_LOAD(a[brev(c, LOGE)], sm[map.at(pre, c << ls)]);
             }
+            bool butterflies_done = false;
             if (ls > 0) {
                 cx<R> w[E];
                 stage_twiddles_of_thread<R, E>(tw + stage_tw_off(LOG2L, k, LOGE), s, r, w);
+#if TB_FMA_BFLY
+                dit_regs_tw<R, E>(a, w);
+                butterflies_done = true;
+#else
 #pragma unroll
                 for (int c = 1; c < E; ++c) a[brev(c, LOGE)] = cmulc(a[brev(c, LOGE)], w[c]);
+#endif
             }
-            dit_regs<R, E>(a);
+            if (!butterflies_done) dit_regs<R, E>(a);
             if (k > 0) {
 #pragma unroll
                 for (int c = 0; c < E; ++c) TB_SM_STORE(sm[map.at(pre, c << ls)], a[c]);
