@@ -36,6 +36,7 @@ static std::atomic<int> g_time_passes{0};
 static std::atomic<int> g_ca_fuse{0};            // 1: pass C of a group + pass A of the next one on its stream as one launch; 2: + async x tile
 static std::atomic<int> g_pdl{1};                // programmatic dependent launch of passes B / C: 0 off, 1 products without group overlap, 2 always
 static std::atomic<int> g_l2_persist_mb{64};     // persisting-L2 carve-out for the two-level workspaces (0 = off); +4 % on config 2
+static std::atomic<int> g_rows_direct{1};        // pass B addresses its workspace rows directly (IO_SPEC path) instead of through the column views
 static std::atomic<int> g_pair_columns{1};       // real columns two per complex transform (0: one per transform, columns numerically independent)
 static std::atomic<int> g_tma{0};                // TMA-staged strided passes (tma_cols.cuh) where eligible; measured, see DESIGN.md
 extern int g_lev_gen;                            // levinson.cu
@@ -626,9 +627,11 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     // ones (2 x 64 MiB of config 3, 256 MiB of config 5) stream through DRAM anyway and a partial window costs them
     // 15-30 % (profiles/experiments_r02.md)
     const size_t ws_in_flight = (size_t)nstr * (size_t)G * Np * sizeof(cx<R>);
-    // ... and only for multi-group products (the overlapped pipeline the window was measured on): a single transform
-    // (factorize, a lone vector) would flip the device-wide limit back and forth between calls for nothing
-    const bool l2win = g_l2_persist_mb.load() > 0 && overlap && ws_in_flight <= ((size_t)g_l2_persist_mb.load() << 20);
+    // ... and only for multi-group products (with or without the stream overlap: pass C of a group finds its workspace
+    // in L2 either way): a single transform (factorize, a lone vector) would flip the device-wide limit back and forth
+    // between calls for nothing
+    const bool multi_group = c.nfft > G && c.do_fwd && c.do_inv;
+    const bool l2win = g_l2_persist_mb.load() > 0 && multi_group && ws_in_flight <= ((size_t)g_l2_persist_mb.load() << 20);
     if (!l2win && ws_in_flight > ((size_t)g_l2_persist_mb.load() << 20))
         release_l2_carveout();              // a carve-out left behind by a smaller product halves the L2 this one sees
     for (int i = 0; i < nstr; ++i) {
@@ -754,6 +757,8 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
             }
             pb.scale = (R)1; pb.alpha = mk<R>(1, 0); pb.beta = mk<R>(0, 0); pb.has_beta = 0;
             pb.colmap = nullptr; pb.col_alpha = nullptr;
+            if (g_rows_direct.load()) { pb.x_mode = IO_SPEC; pb.y_mode = IO_SPEC; }   // full rows, unit epilogue: the plain
+                                                        // load / store path of k_rows (same addresses, no per-element bounds and mode logic)
             if (!c.do_fwd) {             // inverse only: rows come from a layout-order spectrum
                 pb.x = c.nested ? (const void*)(reinterpret_cast<const cx<R>*>(c.x) + (size_t)f0 * Np) : c.x;
                 pb.x_mode = IO_SPEC; pb.spec = nullptr;
@@ -1061,6 +1066,7 @@ int tb200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "l2_persist_mb")) { g_l2_persist_mb = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 1024); return TB200_OK; }
     if (!strcmp(name, "lev_gen")) { g_lev_gen = (int)(value & 1); return TB200_OK; }
     if (!strcmp(name, "prune_half")) { g_prune_half = value ? 1 : 0; return TB200_OK; }
+    if (!strcmp(name, "rows_direct")) { g_rows_direct = value != 0; return TB200_OK; }
     if (!strcmp(name, "pair_columns")) { g_pair_columns = value != 0; return TB200_OK; }
     if (!strcmp(name, "tma")) { g_tma = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 3); return TB200_OK; }   // bit 0: pass A loads, bit 1: pass C stores
     if (!strcmp(name, "overlap_streams")) { g_overlap_streams = (int)std::min<int64_t>(std::max<int64_t>(value, 0), tb200_fact::MAXS); return TB200_OK; }
