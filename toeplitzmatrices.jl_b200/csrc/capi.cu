@@ -631,7 +631,10 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     // in L2 either way): a single transform (factorize, a lone vector) would flip the device-wide limit back and forth
     // between calls for nothing
     const bool multi_group = c.nfft > G && c.do_fwd && c.do_inv;
-    const bool l2win = g_l2_persist_mb.load() > 0 && multi_group && ws_in_flight <= ((size_t)g_l2_persist_mb.load() << 20);
+    // ... and when the spectrum every pass B streams fits beside them (config 3 on one stream: 64 MiB + 64 MiB, 8.2 k -> 7.9 k
+    // solves/s with the window)
+    const bool l2win = g_l2_persist_mb.load() > 0 && multi_group && ws_in_flight <= ((size_t)g_l2_persist_mb.load() << 20) &&
+                       ws_in_flight + (size_t)Np * sizeof(cx<R>) <= ((size_t)104 << 20);
     if (!l2win && ws_in_flight > ((size_t)g_l2_persist_mb.load() << 20))
         release_l2_carveout();              // a carve-out left behind by a smaller product halves the L2 this one sees
     for (int i = 0; i < nstr; ++i) {
