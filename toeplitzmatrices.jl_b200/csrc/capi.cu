@@ -635,7 +635,7 @@ static int run_conv_t(tb200_fact* h, const ConvCall& c, cudaStream_t s) {
     // solves/s with the window)
     const bool l2win = g_l2_persist_mb.load() > 0 && multi_group && ws_in_flight <= ((size_t)g_l2_persist_mb.load() << 20) &&
                        ws_in_flight + (size_t)Np * sizeof(cx<R>) <= ((size_t)104 << 20);
-    if (!l2win && ws_in_flight > ((size_t)g_l2_persist_mb.load() << 20))
+    if (!l2win && (multi_group || ws_in_flight > ((size_t)g_l2_persist_mb.load() << 20)))
         release_l2_carveout();              // a carve-out left behind by a smaller product halves the L2 this one sees
     for (int i = 0; i < nstr; ++i) {
         if (l2win) { apply_l2_window(stream_of[i], scratch_of[i], (size_t)G * Np * sizeof(cx<R>), nstr); w->win_set[i] = true; }
