@@ -222,13 +222,15 @@ int64_t tb200_launch_count(void);
 /* process-wide tuning knobs (defaults are what the measurements in DESIGN.md were taken with):
  *   "group_bytes"      two-level workspace budget per column group (default 32 MiB)
  *   "overlap_streams"  internal streams that alternate column groups (default 2; 0 / 1 = off)
- *   "l2_persist_mb"    persisting-L2 carve-out for the workspaces of overlapped products (default 64; 0 = off)
+ *   "l2_persist_mb"    persisting-L2 carve-out for the workspaces of products with several column groups whose
+ *                      workspaces and spectrum fit L2 together (default 64; 0 = off)
  *   "prune_half"       skip the padding half of the embedding in the strided passes (default 1)
  *   "pdl"              programmatic dependent launch of passes B / C: 0 off, 1 products without group overlap (default), 2 always
  *   "pair_columns"     real columns of a matrix product share one complex transform two by two (default 1).  The pair
  *                      is coupled numerically: a NaN / Inf in one column reaches its partner, and each column's error is
  *                      relative to the larger norm of the pair.  0 transforms every real column alone (the reference's
  *                      independent column loop, src/linearalgebra.jl:95-97) at half the throughput.
+ *   "rows_direct"      pass B addresses its workspace rows directly instead of through the column views (default 1)
  *   "tma"              TMA tensor-box staging of the strided tiles: bit 0 pass A, bit 1 pass C (default 0)
  *   "lev_gen"          Levinson / Durbin in generator form (default 1; 0 = the dot-product kernels)
  *   "time_passes"      bracket every pass with CUDA events for tb200_pass_times (default 0)
