@@ -93,3 +93,18 @@ def test_fft_index_model_two_level(l1, l2, loge):
     Np = 1 << (l1 + l2)
     x = rng.standard_normal(Np) + 1j * rng.standard_normal(Np)
     assert np.allclose(unscramble(two_level_forward(x, l1, l2), l1, l2), np.fft.fft(x), atol=1e-10)
+
+
+def test_every_runtime_option_is_documented_in_the_header():
+    """`tb200_set_option` names parsed in csrc/capi.cu all appear in include/toeplitz_b200.h (the `_f64` / `_f32` pairs are
+    listed there once as `name_f64/f32`)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "toeplitzmatrices.jl_b200", "csrc", "capi.cu")).read()
+    hdr = open(os.path.join(root, "include", "toeplitz_b200.h")).read()
+    names = sorted(set(re.findall(r'strcmp\(name, "([a-z0-9_]+)"\)', src)))
+    assert len(names) >= 15
+    for name in names:
+        stem = re.sub(r"_f(32|64)$", "", name)
+        assert ('"%s"' % name) in hdr or ('"%s_f64/f32"' % stem) in hdr, "option %s is not documented in the header" % name
