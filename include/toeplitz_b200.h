@@ -220,7 +220,7 @@ int tb200_vec_equal(int64_t n, const void* a, int dtype_a, const void* b, int dt
 /* tuning / introspection: number of kernel launches issued by this library so far      */
 int64_t tb200_launch_count(void);
 /* process-wide tuning knobs (defaults are what the measurements in DESIGN.md were taken with):
- *   "group_bytes"      two-level workspace budget per column group (default 32 MiB)
+ *   "group_bytes"      two-level workspace budget per column group (default 48 MiB: one 32-MiB column pair at n = 2^20 Float64)
  *   "overlap_streams"  internal streams that alternate column groups (default 2; 0 / 1 = off)
  *   "l2_persist_mb"    persisting-L2 carve-out for the workspaces of products with several column groups whose
  *                      workspaces and spectrum fit L2 together (default 64; 0 = off)
