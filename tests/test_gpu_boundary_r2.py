@@ -6,8 +6,8 @@
   src/ToeplitzMatrices.jl:97-101, forbids this).
 * destroy right after an asynchronous product on a non-default stream (stream-ordered release).
 * `tb200_mul_host` straight after an asynchronous `factorize` (waits for the spectrum by event).
-* the C ABI's own NCCL communicator (`tb200_comm_*`), single-device group here; the multi-GPU form runs in
-  `tests/test_gpu_multi.py` when more than one device is visible.
+* the C ABI's own NCCL communicator (`tb200_comm_*`), single-device group, and one process driving two GPUs
+  (`test_comm_two_devices_single_process`, skipped on a one-GPU box).
 """
 import ctypes
 
